@@ -1,0 +1,203 @@
+// Host side of the fused MLP: program construction, operand packing.
+#include <math.h>
+#include <string.h>
+#include "common.cuh"
+#include "mlp_common.cuh"
+
+namespace fs {
+
+int build_program(const fsnerf_net_cfg* cfg, MlpProgram* P) {
+  FS_REQUIRE(cfg && P, "net cfg: null");
+  FS_REQUIRE(cfg->d_hidden == 256, "net cfg: d_hidden must be 256 (tcgen05 tile width), got %d",
+             cfg->d_hidden);
+  FS_REQUIRE(cfg->n_layers >= 2 && cfg->n_layers + 2 <= kMaxGemm, "net cfg: n_layers must be in [2,%d]",
+             kMaxGemm - 2);
+  FS_REQUIRE(cfg->n_freqs_pos >= 0 && cfg->n_freqs_pos <= kMaxFreqs, "net cfg: n_freqs_pos must be <= 10");
+  FS_REQUIRE(cfg->n_freqs_dir >= 0 && cfg->n_freqs_dir <= kMaxFreqs, "net cfg: n_freqs_dir must be <= 10");
+  FS_REQUIRE((cfg->skip_mask >> (cfg->n_layers - 1)) == 0,
+             "net cfg: skip on or after the last hidden layer is unsupported");
+  memset(P, 0, sizeof(*P));
+  const int H = cfg->d_hidden, n = cfg->n_layers;
+  P->n_hidden = n;
+  P->n_freqs_pos = cfg->n_freqs_pos;
+  P->n_freqs_dir = cfg->n_freqs_dir;
+  P->d_pos = 3 * (1 + 2 * cfg->n_freqs_pos);
+  P->d_dir = 3 * (1 + 2 * cfg->n_freqs_dir);
+  // frequencies exactly as torch builds them (src/core/models.py:30-34)
+  for (int pass = 0; pass < 2; ++pass) {
+    int L = pass ? cfg->n_freqs_dir : cfg->n_freqs_pos;
+    float* f = pass ? P->freq_dir : P->freq_pos;
+    for (int k = 0; k < L; ++k) {
+      if (cfg->log_space) {
+        f[k] = ldexpf(1.0f, k);
+      } else {
+        // torch.linspace(1, 2^(L-1), L): symmetric evaluation around the midpoint
+        float start = 1.0f, end = ldexpf(1.0f, L - 1);
+        float step = (L > 1) ? (end - start) / (float)(L - 1) : 0.0f;
+        f[k] = (k < L / 2) ? start + step * (float)k : end - step * (float)(L - 1 - k);
+      }
+    }
+  }
+  int64_t off = 0;
+  int blk = 0;
+  int stash = 0;
+  P->stash_aux_pos_off = stash;
+  stash += kChunkBytes;
+  int g = 0;
+  for (int i = 0; i < n; ++i, ++g) {
+    GemmLayer& L = P->layer[g];
+    bool first = (i == 0);
+    bool skip_in = !first && ((cfg->skip_mask >> (i - 1)) & 1);
+    L.n_act_chunks = first ? 0 : H / 64;
+    L.use_aux = (first || skip_in) ? 1 : 0;
+    L.n_halves = H / 128;
+    L.epi = (i == n - 1) ? EPI_RELU_SIGMA : EPI_RELU;
+    L.ld = first ? P->d_pos : (skip_in ? H + P->d_pos : H);
+    L.w_off = (int)off;
+    off += (int64_t)H * L.ld;
+    L.bias_off = (int)off;
+    off += H;
+    L.first_block = blk;
+    blk += (L.n_act_chunks + L.use_aux) * L.n_halves;
+    L.stash_off = stash;
+    stash += (H / 64) * kChunkBytes;
+  }
+  P->sigma_w_off = (int)off; off += H;
+  P->sigma_b_off = (int)off; off += 1;
+  P->n_blocks_fwd_density = blk;
+  {  // connection
+    GemmLayer& L = P->layer[g++];
+    L.n_act_chunks = H / 64; L.use_aux = 0; L.n_halves = H / 128; L.epi = EPI_CONN;
+    L.ld = H; L.w_off = (int)off; off += (int64_t)H * H; L.bias_off = (int)off; off += H;
+    L.first_block = blk; blk += L.n_act_chunks * L.n_halves;
+    L.stash_off = stash; stash += (H / 64) * kChunkBytes;
+  }
+  P->stash_aux_dir_off = stash;
+  stash += kChunkBytes;
+  {  // branch
+    GemmLayer& L = P->layer[g++];
+    L.n_act_chunks = H / 64; L.use_aux = 1; L.n_halves = (H / 2) / 128; L.epi = EPI_BRANCH;
+    L.ld = H + P->d_dir; L.w_off = (int)off; off += (int64_t)(H / 2) * L.ld;
+    L.bias_off = (int)off; off += H / 2;
+    L.first_block = blk; blk += (L.n_act_chunks + 1) * L.n_halves;
+    L.stash_off = stash; stash += ((H / 2) / 64) * kChunkBytes;
+  }
+  P->rgb_w_off = (int)off; off += 3 * (H / 2);
+  P->rgb_b_off = (int)off; off += 3;
+  P->n_gemm = g;
+  P->n_blocks_fwd = blk;
+  P->n_params = off;
+  P->stash_tile_bytes = stash;
+  // dgrad (W^T) blocks, in backward consumption order: branch, conn, hidden n-1 .. 1
+  for (int gi = P->n_gemm - 1; gi >= 1; --gi) {
+    GemmLayer& L = P->layer[gi];
+    int n_out = L.n_halves * 128;
+    L.bwd_first_block = blk;
+    L.bwd_n_halves = H / 128;  // gradient w.r.t. the first d_hidden inputs only
+    L.bwd_n_chunks = n_out / 64;
+    blk += L.bwd_n_halves * L.bwd_n_chunks;
+  }
+  P->layer[0].bwd_first_block = -1;
+  P->n_blocks_bwd = blk - P->n_blocks_fwd;
+  P->packed_bytes = (int64_t)blk * kBlockBytes;
+  return FSNERF_OK;
+}
+
+namespace {
+
+struct PackBlk {
+  int w_off;
+  short ld, row0, col0, nrows, ncols, transposed;
+};
+constexpr int kMaxPackBlk = 192;
+struct PackTable {
+  int n;
+  PackBlk b[kMaxPackBlk];
+};
+
+__global__ void __launch_bounds__(256)
+pack_kernel(const __grid_constant__ PackTable T, const float* __restrict__ params,
+            uint8_t* __restrict__ packed) {
+  const PackBlk b = T.b[blockIdx.x];
+  uint8_t* dst = packed + (size_t)blockIdx.x * kBlockBytes;
+  const float* W = params + b.w_off;
+  for (int u = threadIdx.x; u < 1024; u += blockDim.x) {
+    int i = u >> 3, j = u & 7;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int kk = j * 8 + e;
+      float x = 0.f;
+      if (i < b.nrows && kk < b.ncols) {
+        x = b.transposed ? W[(size_t)(b.row0 + kk) * b.ld + (b.col0 + i)]
+                         : W[(size_t)(b.row0 + i) * b.ld + (b.col0 + kk)];
+      }
+      v[e] = x;
+    }
+    uint4 w4 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                          pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    *reinterpret_cast<uint4*>(dst + sw128_off(i, j)) = w4;
+  }
+}
+
+}  // namespace
+}  // namespace fs
+
+using namespace fs;
+
+extern "C" int64_t fsnerf_mlp_param_count(const fsnerf_net_cfg* cfg) {
+  MlpProgram P;
+  if (build_program(cfg, &P) != FSNERF_OK) return -1;
+  return P.n_params;
+}
+extern "C" int64_t fsnerf_mlp_packed_bytes(const fsnerf_net_cfg* cfg) {
+  MlpProgram P;
+  if (build_program(cfg, &P) != FSNERF_OK) return -1;
+  return P.packed_bytes;
+}
+extern "C" int64_t fsnerf_mlp_stash_bytes(const fsnerf_net_cfg* cfg, int64_t n_samples) {
+  MlpProgram P;
+  if (build_program(cfg, &P) != FSNERF_OK) return -1;
+  int64_t tiles = (n_samples + kTileM - 1) / kTileM;
+  return tiles * (int64_t)P.stash_tile_bytes;
+}
+
+extern "C" int fsnerf_mlp_pack(const fsnerf_net_cfg* cfg, const float* params, void* packed,
+                               void* stream) {
+  MlpProgram P;
+  int rc = build_program(cfg, &P);
+  if (rc != FSNERF_OK) return rc;
+  FS_REQUIRE(params && packed, "mlp_pack: null pointer");
+  FS_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127) == 0, "mlp_pack: packed must be 128B aligned");
+  static PackTable T;  // host staging (one host thread per device, see header)
+  T.n = 0;
+  for (int g = 0; g < P.n_gemm; ++g) {
+    const GemmLayer& L = P.layer[g];
+    int n_out = L.n_halves * 128;
+    int nchunks = L.n_act_chunks + L.use_aux;
+    int n_act_cols = L.n_act_chunks * 64;
+    for (int c = 0; c < nchunks; ++c)
+      for (int nh = 0; nh < L.n_halves; ++nh) {
+        PackBlk& b = T.b[T.n++];
+        b.w_off = L.w_off; b.ld = (short)L.ld; b.transposed = 0;
+        b.row0 = (short)(nh * 128); b.nrows = (short)((n_out - nh * 128) < 128 ? (n_out - nh * 128) : 128);
+        b.col0 = (short)(c * 64);
+        b.ncols = (short)((c < L.n_act_chunks) ? 64 : (L.ld - n_act_cols));
+      }
+  }
+  FS_REQUIRE(T.n == P.n_blocks_fwd, "mlp_pack: internal block count mismatch (%d vs %d)", T.n, P.n_blocks_fwd);
+  for (int g = P.n_gemm - 1; g >= 1; --g) {
+    const GemmLayer& L = P.layer[g];
+    for (int c = 0; c < L.bwd_n_chunks; ++c)
+      for (int nh = 0; nh < L.bwd_n_halves; ++nh) {
+        PackBlk& b = T.b[T.n++];
+        b.w_off = L.w_off; b.ld = (short)L.ld; b.transposed = 1;
+        b.row0 = (short)(c * 64); b.ncols = 64;   // K = output features
+        b.col0 = (short)(nh * 128); b.nrows = 128;  // rows = input features
+      }
+  }
+  FS_REQUIRE(T.n == P.n_blocks_fwd + P.n_blocks_bwd && T.n <= kMaxPackBlk,
+             "mlp_pack: internal block count mismatch");
+  pack_kernel<<<T.n, 256, 0, (cudaStream_t)stream>>>(T, params, reinterpret_cast<uint8_t*>(packed));
+  return fsnerf_check_launch("mlp_pack");
+}

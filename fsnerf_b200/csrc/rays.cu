@@ -1,0 +1,274 @@
+// Kernel family (1): ray generation (+NDC, +rgb gather), stratified sampling,
+// hierarchical sample_pdf.  HBM/latency-bound integer + fp32 bookkeeping.
+//
+// Every fp32 product/sum whose rounding reaches an integer decision (pixel
+// bookkeeping, searchsorted index, sort permutation) is written with the
+// _rn intrinsics so nvcc cannot contract it into an FMA: oracle/rays.py and
+// oracle/sampling.py restate the same op order in numpy and must agree bit
+// for bit.
+#include "common.cuh"
+#include "../../include/fsnerf_b200.h"
+
+namespace {
+
+// reference: src/utils/utilities.py:54-82 (get_rays) and :102-120 (to_ndc)
+__device__ __forceinline__ void ndc_warp(float& ox, float& oy, float& oz, float& dx, float& dy,
+                                         float& dz, float near, float sx, float sy) {
+  float t = __fdiv_rn(-__fadd_rn(near, oz), dz);
+  ox = __fadd_rn(ox, __fmul_rn(t, dx));
+  oy = __fadd_rn(oy, __fmul_rn(t, dy));
+  oz = __fadd_rn(oz, __fmul_rn(t, dz));
+  float o0 = __fdiv_rn(__fmul_rn(sx, ox), oz);
+  float o1 = __fdiv_rn(__fmul_rn(sy, oy), oz);
+  float o2 = __fadd_rn(1.0f, __fdiv_rn(__fmul_rn(2.0f, near), oz));
+  float d0 = __fmul_rn(sx, __fsub_rn(__fdiv_rn(dx, dz), __fdiv_rn(ox, oz)));
+  float d1 = __fmul_rn(sy, __fsub_rn(__fdiv_rn(dy, dz), __fdiv_rn(oy, oz)));
+  float d2 = __fdiv_rn(__fmul_rn(-2.0f, near), oz);
+  ox = o0; oy = o1; oz = o2; dx = d0; dy = d1; dz = d2;
+}
+
+__global__ void gen_rays_kernel(const float* __restrict__ poses, int n_views, int pose_rows, int H,
+                                int W, float focal, const int64_t* __restrict__ pixel_ids,
+                                int64_t first_id, int64_t n_rays, int ndc, float near, float sx,
+                                float sy, const float* __restrict__ images,
+                                float* __restrict__ rays_o, float* __restrict__ rays_d,
+                                float* __restrict__ rgb_gt) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rays) return;
+  int64_t p = pixel_ids ? pixel_ids[i] : first_id + i;
+  int64_t hw = (int64_t)H * W;
+  int v = (int)(p / hw);
+  int rem = (int)(p - (int64_t)v * hw);
+  int h = rem / W, w = rem - h * W;
+  const float* P = poses + (int64_t)v * pose_rows * 4;
+  float x = __fdiv_rn(__fsub_rn((float)w, W * 0.5f), focal);
+  float y = -__fdiv_rn(__fsub_rn((float)h, H * 0.5f), focal);
+  float z = -1.0f;
+  float n = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+  x = __fdiv_rn(x, n); y = __fdiv_rn(y, n); z = __fdiv_rn(z, n);
+  float d[3], o[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    d[a] = __fadd_rn(__fadd_rn(__fmul_rn(x, P[a * 4 + 0]), __fmul_rn(y, P[a * 4 + 1])),
+                     __fmul_rn(z, P[a * 4 + 2]));
+    o[a] = P[a * 4 + 3];
+  }
+  if (ndc) ndc_warp(o[0], o[1], o[2], d[0], d[1], d[2], near, sx, sy);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    rays_o[i * 3 + a] = o[a];
+    rays_d[i * 3 + a] = d[a];
+  }
+  if (images && rgb_gt) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) rgb_gt[i * 3 + a] = images[p * 3 + a];
+  }
+}
+
+__global__ void to_ndc_kernel(const float* __restrict__ ro, const float* __restrict__ rd, int64_t n,
+                              float near, float sx, float sy, float* __restrict__ no,
+                              float* __restrict__ nd) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float ox = ro[i * 3], oy = ro[i * 3 + 1], oz = ro[i * 3 + 2];
+  float dx = rd[i * 3], dy = rd[i * 3 + 1], dz = rd[i * 3 + 2];
+  ndc_warp(ox, oy, oz, dx, dy, dz, near, sx, sy);
+  no[i * 3] = ox; no[i * 3 + 1] = oy; no[i * 3 + 2] = oz;
+  nd[i * 3] = dx; nd[i * 3 + 1] = dy; nd[i * 3 + 2] = dz;
+}
+
+// ---- stratified (oracle/sampling.py:stratified) ----
+__device__ __forceinline__ float strat_z(int i, int S, float near, float far) {
+  float t = (S > 1) ? __fdiv_rn((float)i, (float)(S - 1)) : 0.0f;
+  return __fadd_rn(__fmul_rn(near, __fsub_rn(1.0f, t)), __fmul_rn(far, t));
+}
+__device__ __forceinline__ float strat_point(int i, int S, float near, float far, const float* u) {
+  float z = strat_z(i, S, near, far);
+  if (!u) return z;
+  float lower = (i == 0) ? z : __fmul_rn(0.5f, __fadd_rn(z, strat_z(i - 1, S, near, far)));
+  float upper = (i == S - 1) ? z : __fmul_rn(0.5f, __fadd_rn(strat_z(i + 1, S, near, far), z));
+  return __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), u[i]));
+}
+
+__global__ void stratified_kernel(int64_t n_rays, int S, float near, float far,
+                                  const float* __restrict__ u, float* __restrict__ ts,
+                                  float* __restrict__ te) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_rays * S) return;
+  int64_t r = idx / S;
+  int i = (int)(idx - r * S);
+  const float* ur = u ? u + r * S : nullptr;
+  ts[idx] = strat_point(i, S, near, far, ur);
+  te[idx] = (i == S - 1) ? far : strat_point(i + 1, S, near, far, ur);
+}
+
+// ---- sample_pdf (Appendix B2; oracle/sampling.py:sample_pdf) --------------
+// One warp per ray.  CDF in "warp-tree order": lane l owns E consecutive
+// weights; lane-local sums sequential, total by xor-butterfly, cross-lane
+// prefix by Kogge-Stone.
+constexpr int kPdfMaxE = 8;  // n_coarse - 2 <= 256
+constexpr int kPdfWarps = 4;
+
+__global__ void __launch_bounds__(kPdfWarps * 32)
+sample_pdf_kernel(int64_t n_rays, int Sc, int Sf, const float* __restrict__ z_coarse,
+                  const float* __restrict__ w_coarse, const float* __restrict__ u, float far,
+                  float* __restrict__ samples, int32_t* __restrict__ inds_out,
+                  int32_t* __restrict__ perm_out, float* __restrict__ ts, float* __restrict__ te) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * kPdfWarps + warp;
+  const int nb = Sc - 1, nw = Sc - 2, ntot = Sc + Sf;
+  const int per_warp = 2 * nb + 2 * ntot;
+  float* cdf = smem + warp * per_warp;  // [nb]
+  float* bins = cdf + nb;               // [nb]
+  float* cat = bins + nb;               // [ntot]
+  float* sorted = cat + ntot;           // [ntot]
+  if (r >= n_rays) return;
+  const float* zc = z_coarse + r * Sc;
+  const float* wc = w_coarse + r * Sc;
+  const int E = (nw + 31) / 32;
+
+  for (int j = lane; j < nb; j += 32) bins[j] = __fmul_rn(0.5f, __fadd_rn(zc[j + 1], zc[j]));
+  for (int j = lane; j < Sc; j += 32) cat[j] = zc[j];
+
+  float wp[kPdfMaxE];
+  float s = 0.0f;
+#pragma unroll
+  for (int e = 0; e < kPdfMaxE; ++e) {
+    if (e < E) {
+      int j = lane * E + e;
+      wp[e] = (j < nw) ? __fadd_rn(wc[j + 1], 1e-5f) : 0.0f;
+      s = (e == 0) ? wp[0] : __fadd_rn(s, wp[e]);
+    }
+  }
+  float tot = s;
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) tot = __fadd_rn(tot, __shfl_xor_sync(0xffffffffu, tot, m));
+  float loc[kPdfMaxE];
+#pragma unroll
+  for (int e = 0; e < kPdfMaxE; ++e) {
+    if (e < E) {
+      float pdf = __fdiv_rn(wp[e], tot);
+      loc[e] = (e == 0) ? pdf : __fadd_rn(loc[(e + kPdfMaxE - 1) % kPdfMaxE], pdf);
+    }
+  }
+  float T = loc[0];
+#pragma unroll
+  for (int e = 1; e < kPdfMaxE; ++e)
+    if (e < E) T = loc[e];
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    float up = __shfl_up_sync(0xffffffffu, T, d);
+    if (lane >= d) T = __fadd_rn(T, up);
+  }
+  float excl = __shfl_up_sync(0xffffffffu, T, 1);
+  if (lane == 0) {
+    excl = 0.0f;
+    cdf[0] = 0.0f;
+  }
+#pragma unroll
+  for (int e = 0; e < kPdfMaxE; ++e) {
+    if (e < E) {
+      int j = lane * E + e;
+      if (j < nw) cdf[j + 1] = (e == E - 1) ? T : __fadd_rn(excl, loc[e]);
+    }
+  }
+  __syncwarp();
+
+  for (int k = lane; k < Sf; k += 32) {
+    float uk = u ? u[r * Sf + k] : (Sf > 1 ? __fdiv_rn((float)k, (float)(Sf - 1)) : 0.0f);
+    // searchsorted(right=True): number of cdf entries <= uk (cdf is increasing)
+    int lo = 0, hi = nb;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (cdf[mid] <= uk) lo = mid + 1; else hi = mid;
+    }
+    int ind = lo;
+    int below = max(ind - 1, 0), above = min(ind, nb - 1);
+    float c0 = cdf[below], c1 = cdf[above], b0 = bins[below], b1 = bins[above];
+    float denom = __fsub_rn(c1, c0);
+    if (denom < 1e-5f) denom = 1.0f;
+    float t = __fdiv_rn(__fsub_rn(uk, c0), denom);
+    float smp = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+    cat[Sc + k] = smp;
+    if (samples) samples[r * Sf + k] = smp;
+    if (inds_out) inds_out[r * Sf + k] = ind;
+  }
+  __syncwarp();
+
+  // stable rank sort of cat[0..ntot): rank = #{j: cat[j] < v or (== and j < i)}
+  for (int i = lane; i < ntot; i += 32) {
+    float v = cat[i];
+    int rank = 0;
+    for (int j = 0; j < ntot; ++j) {
+      float c = cat[j];
+      rank += (c < v || (c == v && j < i)) ? 1 : 0;
+    }
+    sorted[rank] = v;
+    if (perm_out) perm_out[r * ntot + rank] = i;
+  }
+  __syncwarp();
+  for (int k = lane; k < ntot; k += 32) {
+    ts[r * ntot + k] = sorted[k];
+    te[r * ntot + k] = (k == ntot - 1) ? far : sorted[k + 1];
+  }
+}
+
+}  // namespace
+
+extern "C" int fsnerf_gen_rays(const float* poses, int n_views, int pose_rows, int H, int W,
+                               float focal, const int64_t* pixel_ids, int64_t first_id,
+                               int64_t n_rays, int ndc, float ndc_near, float ndc_sx, float ndc_sy,
+                               const float* images, float* rays_o, float* rays_d, float* rgb_gt,
+                               void* stream) {
+  FS_REQUIRE(poses && rays_o && rays_d, "gen_rays: null pointer");
+  FS_REQUIRE(pose_rows == 3 || pose_rows == 4, "gen_rays: pose_rows must be 3 or 4");
+  FS_REQUIRE(H > 0 && W > 0 && n_views > 0 && n_rays >= 0, "gen_rays: bad sizes");
+  if (n_rays == 0) return FSNERF_OK;
+  int threads = 256;
+  int64_t blocks = (n_rays + threads - 1) / threads;
+  gen_rays_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+      poses, n_views, pose_rows, H, W, focal, pixel_ids, first_id, n_rays, ndc, ndc_near, ndc_sx,
+      ndc_sy, images, rays_o, rays_d, rgb_gt);
+  return fsnerf_check_launch("gen_rays");
+}
+
+extern "C" int fsnerf_to_ndc(const float* rays_o, const float* rays_d, int64_t n_rays, float near,
+                             float sx, float sy, float* ndc_o, float* ndc_d, void* stream) {
+  FS_REQUIRE(rays_o && rays_d && ndc_o && ndc_d, "to_ndc: null pointer");
+  if (n_rays == 0) return FSNERF_OK;
+  int threads = 256;
+  int64_t blocks = (n_rays + threads - 1) / threads;
+  to_ndc_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(rays_o, rays_d, n_rays,
+                                                                        near, sx, sy, ndc_o, ndc_d);
+  return fsnerf_check_launch("to_ndc");
+}
+
+extern "C" int fsnerf_sample_stratified(int64_t n_rays, int n_samples, float near, float far,
+                                        const float* u, float* t_starts, float* t_ends,
+                                        void* stream) {
+  FS_REQUIRE(t_starts && t_ends, "sample_stratified: null output");
+  FS_REQUIRE(n_samples >= 1 && n_rays >= 0, "sample_stratified: bad sizes");
+  if (n_rays == 0) return FSNERF_OK;
+  int64_t n = n_rays * n_samples;
+  int threads = 256;
+  stratified_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+      n_rays, n_samples, near, far, u, t_starts, t_ends);
+  return fsnerf_check_launch("sample_stratified");
+}
+
+extern "C" int fsnerf_sample_pdf(int64_t n_rays, int n_coarse, int n_fine, const float* z_coarse,
+                                 const float* w_coarse, const float* u, float far, float* samples,
+                                 int32_t* inds, int32_t* perm, float* t_starts, float* t_ends,
+                                 void* stream) {
+  FS_REQUIRE(z_coarse && w_coarse && t_starts && t_ends, "sample_pdf: null pointer");
+  FS_REQUIRE(n_coarse >= 3 && n_coarse - 2 <= 32 * kPdfMaxE, "sample_pdf: n_coarse must be in [3,258]");
+  FS_REQUIRE(n_fine >= 1 && n_fine <= 1024, "sample_pdf: n_fine must be in [1,1024]");
+  if (n_rays == 0) return FSNERF_OK;
+  size_t smem = (size_t)kPdfWarps * (2 * (n_coarse - 1) + 2 * (n_coarse + n_fine)) * sizeof(float);
+  FS_REQUIRE(smem <= 48 * 1024, "sample_pdf: n_coarse+n_fine too large for shared memory");
+  int64_t blocks = (n_rays + kPdfWarps - 1) / kPdfWarps;
+  sample_pdf_kernel<<<(unsigned)blocks, kPdfWarps * 32, smem, (cudaStream_t)stream>>>(
+      n_rays, n_coarse, n_fine, z_coarse, w_coarse, u, far, samples, inds, perm, t_starts, t_ends);
+  return fsnerf_check_launch("sample_pdf");
+}

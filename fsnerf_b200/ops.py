@@ -1,0 +1,212 @@
+"""Thin torch-tensor wrappers over the C ABI (device memory + stream plumbing
+only; all arithmetic happens in libfsnerf_b200.so).  Every function requires
+CUDA tensors; there is no CPU path."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import NetCfg, check, ptr
+
+COMP_SIGMA_RELU = 1
+COMP_DEPTH_UNNORM = 2
+COMP_PRODUCT_TRANS = 4
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t, name):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.FsnerfError(f"{name}: expected a CUDA tensor (no CPU fallback)")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.contiguous().float()
+    return t
+
+
+def require_device(dev=None):
+    dev = torch.cuda.current_device() if dev is None else dev
+    check(_lib.load().fsnerf_device_ok(int(dev)), "fsnerf_device_ok")
+
+
+# ------------------------------------------------------------------ rays
+def gen_rays(poses, H, W, focal, pixel_ids=None, first_id=0, n_rays=None, ndc=False,
+             ndc_near=1.0, images=None):
+    """poses [V,3|4,4] f32 cuda; pixel_ids int64 [R] or None (first_id + arange(n_rays)).
+    -> rays_o [R,3], rays_d [R,3], rgb_gt [R,3] | None"""
+    poses = _f32c(poses, "poses")
+    if poses.dim() == 2:
+        poses = poses[None]
+    V, rows = poses.shape[0], poses.shape[1]
+    if pixel_ids is not None:
+        pixel_ids = pixel_ids.contiguous().to(torch.int64)
+        n_rays = pixel_ids.numel()
+    dev = poses.device
+    rays_o = torch.empty(n_rays, 3, device=dev)
+    rays_d = torch.empty(n_rays, 3, device=dev)
+    images = _f32c(images, "images")
+    rgb = torch.empty(n_rays, 3, device=dev) if images is not None else None
+    sx = -1.0 / (W / (2.0 * focal))
+    sy = -1.0 / (H / (2.0 * focal))
+    check(_lib.load().fsnerf_gen_rays(ptr(poses), V, rows, H, W, float(focal), ptr(pixel_ids),
+                                      int(first_id), int(n_rays), int(ndc), float(ndc_near), sx, sy,
+                                      ptr(images), ptr(rays_o), ptr(rays_d), ptr(rgb), _stream()),
+          "fsnerf_gen_rays")
+    return rays_o, rays_d, rgb
+
+
+def to_ndc(rays_o, rays_d, H, W, focal, near):
+    ro, rd = _f32c(rays_o.reshape(-1, 3), "rays_o"), _f32c(rays_d.reshape(-1, 3), "rays_d")
+    no, nd = torch.empty_like(ro), torch.empty_like(rd)
+    sx = -1.0 / (W / (2.0 * focal))
+    sy = -1.0 / (H / (2.0 * focal))
+    check(_lib.load().fsnerf_to_ndc(ptr(ro), ptr(rd), ro.shape[0], float(near), sx, sy, ptr(no),
+                                    ptr(nd), _stream()), "fsnerf_to_ndc")
+    return no.reshape(rays_o.shape), nd.reshape(rays_d.shape)
+
+
+def sample_stratified(n_rays, n_samples, near, far, u=None, device=None):
+    u = _f32c(u, "u")
+    dev = u.device if u is not None else device
+    ts = torch.empty(n_rays, n_samples, device=dev)
+    te = torch.empty(n_rays, n_samples, device=dev)
+    check(_lib.load().fsnerf_sample_stratified(n_rays, n_samples, float(near), float(far), ptr(u),
+                                               ptr(ts), ptr(te), _stream()), "fsnerf_sample_stratified")
+    return ts, te
+
+
+def sample_pdf(z_coarse, w_coarse, n_fine, far, u=None, want_aux=True):
+    z, w, u = _f32c(z_coarse, "z_coarse"), _f32c(w_coarse, "w_coarse"), _f32c(u, "u")
+    R, Sc = z.shape
+    dev = z.device
+    ts = torch.empty(R, Sc + n_fine, device=dev)
+    te = torch.empty(R, Sc + n_fine, device=dev)
+    samples = torch.empty(R, n_fine, device=dev) if want_aux else None
+    inds = torch.empty(R, n_fine, device=dev, dtype=torch.int32) if want_aux else None
+    perm = torch.empty(R, Sc + n_fine, device=dev, dtype=torch.int32) if want_aux else None
+    check(_lib.load().fsnerf_sample_pdf(R, Sc, n_fine, ptr(z), ptr(w), ptr(u), float(far),
+                                        ptr(samples), ptr(inds), ptr(perm), ptr(ts), ptr(te),
+                                        _stream()), "fsnerf_sample_pdf")
+    return ts, te, samples, inds, perm
+
+
+# ------------------------------------------------------------ compositing
+def composite_forward(raw, t_starts, t_ends, bkgd=None, delta_scale=None, flags=0, extras=False):
+    raw, ts, te = _f32c(raw, "raw"), _f32c(t_starts, "t_starts"), _f32c(t_ends, "t_ends")
+    R, S = ts.shape
+    dev = raw.device
+    rgb = torch.empty(R, 3, device=dev)
+    op = torch.empty(R, 1, device=dev)
+    dp = torch.empty(R, 1, device=dev)
+    w = torch.empty(R, S, device=dev)
+    al = torch.empty(R, S, device=dev) if extras else None
+    tr = torch.empty(R, S, device=dev) if extras else None
+    check(_lib.load().fsnerf_composite_forward(R, S, ptr(raw), ptr(ts), ptr(te),
+                                               ptr(_f32c(delta_scale, "delta_scale")),
+                                               ptr(_f32c(bkgd, "bkgd")), flags, ptr(rgb), ptr(op),
+                                               ptr(dp), ptr(w), ptr(al), ptr(tr), _stream()),
+          "fsnerf_composite_forward")
+    return rgb, op, dp, w, al, tr
+
+
+def composite_backward(raw, t_starts, t_ends, d_rgb, d_opacity=None, d_depth=None, d_weights=None,
+                       bkgd=None, delta_scale=None, flags=0, want_d_bkgd=False):
+    raw, ts, te = _f32c(raw, "raw"), _f32c(t_starts, "t_starts"), _f32c(t_ends, "t_ends")
+    R, S = ts.shape
+    d_raw = torch.empty(R, S, 4, device=raw.device)
+    d_bkgd = torch.zeros(3, device=raw.device) if want_d_bkgd else None
+    check(_lib.load().fsnerf_composite_backward(
+        R, S, ptr(raw), ptr(ts), ptr(te), ptr(_f32c(delta_scale, "delta_scale")),
+        ptr(_f32c(bkgd, "bkgd")), flags, ptr(_f32c(d_rgb, "d_rgb")),
+        ptr(_f32c(d_opacity, "d_opacity")), ptr(_f32c(d_depth, "d_depth")),
+        ptr(_f32c(d_weights, "d_weights")), ptr(d_raw), ptr(d_bkgd), _stream()),
+        "fsnerf_composite_backward")
+    return d_raw, d_bkgd
+
+
+# -------------------------------------------------------------------- MLP
+def make_cfg(n_layers=8, d_hidden=256, skip=(4,), n_freqs_pos=10, n_freqs_dir=4, log_space=True):
+    mask = 0
+    for s in skip:
+        mask |= 1 << int(s)
+    return NetCfg(n_layers, d_hidden, mask, n_freqs_pos, n_freqs_dir, int(bool(log_space)))
+
+
+def mlp_param_count(cfg):
+    n = _lib.load().fsnerf_mlp_param_count(C.byref(cfg))
+    if n < 0:
+        check(-1, "fsnerf_mlp_param_count")
+    return n
+
+
+def mlp_packed_bytes(cfg):
+    n = _lib.load().fsnerf_mlp_packed_bytes(C.byref(cfg))
+    if n < 0:
+        check(-1, "fsnerf_mlp_packed_bytes")
+    return n
+
+
+def mlp_stash_bytes(cfg, n_samples):
+    return _lib.load().fsnerf_mlp_stash_bytes(C.byref(cfg), int(n_samples))
+
+
+def mlp_bwd_workspace_bytes(cfg, n_samples):
+    return _lib.load().fsnerf_mlp_bwd_workspace_bytes(C.byref(cfg), int(n_samples))
+
+
+def mlp_pack(cfg, params, packed=None):
+    params = _f32c(params, "params")
+    if packed is None:
+        packed = torch.empty(mlp_packed_bytes(cfg), dtype=torch.uint8, device=params.device)
+    check(_lib.load().fsnerf_mlp_pack(C.byref(cfg), ptr(params), ptr(packed), _stream()),
+          "fsnerf_mlp_pack")
+    return packed
+
+
+def mlp_forward(cfg, params, packed, *, rays_o=None, rays_d=None, t_starts=None, t_ends=None,
+                x=None, dirs=None, mask_pos=None, mask_dir=None, density_only=False, stash=None,
+                out=None):
+    """Either (rays_o, rays_d, t_starts[R,S], t_ends[R,S]) or (x[P,3], dirs[P,3]|None)."""
+    params = _f32c(params, "params")
+    if x is not None:
+        x, dirs = _f32c(x, "x"), _f32c(dirs, "dirs")
+        P, S = x.shape[0], 1
+    else:
+        rays_o, rays_d = _f32c(rays_o, "rays_o"), _f32c(rays_d, "rays_d")
+        t_starts, t_ends = _f32c(t_starts, "t_starts"), _f32c(t_ends, "t_ends")
+        P, S = t_starts.numel(), t_starts.shape[-1]
+    if out is None:
+        out = torch.empty((P,) if density_only else (P, 4), device=params.device)
+    check(_lib.load().fsnerf_mlp_forward(
+        C.byref(cfg), ptr(params), ptr(packed), P, S, ptr(rays_o), ptr(rays_d), ptr(t_starts),
+        ptr(t_ends), ptr(x), ptr(dirs), ptr(_f32c(mask_pos, "mask_pos")),
+        ptr(_f32c(mask_dir, "mask_dir")), int(density_only), ptr(out), ptr(stash), _stream()),
+        "fsnerf_mlp_forward")
+    return out
+
+
+def mlp_backward(cfg, params, packed, n_samples, stash, out, d_out, grads, workspace,
+                 density_only=False):
+    check(_lib.load().fsnerf_mlp_backward(
+        C.byref(cfg), ptr(params), ptr(packed), int(n_samples), ptr(stash), ptr(out),
+        ptr(_f32c(d_out, "d_out")), int(density_only), ptr(grads), ptr(workspace), _stream()),
+        "fsnerf_mlp_backward")
+    return grads
+
+
+# ------------------------------------------------------------- train step
+def mse_loss_grad(rgb, gt, grad_scale, loss_sum, want_grad=True):
+    rgb, gt = _f32c(rgb, "rgb"), _f32c(gt, "gt")
+    d = torch.empty_like(rgb) if want_grad else None
+    check(_lib.load().fsnerf_mse_loss_grad(rgb.numel(), ptr(rgb), ptr(gt), float(grad_scale),
+                                           ptr(loss_sum), ptr(d), _stream()), "fsnerf_mse_loss_grad")
+    return d
+
+
+def adam_step(params, grads, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
+    check(_lib.load().fsnerf_adam_step(params.numel(), ptr(params), ptr(grads), ptr(m), ptr(v),
+                                       float(lr), beta1, beta2, eps, int(step), _stream()),
+          "fsnerf_adam_step")

@@ -1,0 +1,145 @@
+/* fsnerf_b200 — C ABI of the B200-native fs-nerf ray-march hot path.
+ *
+ * The reference (a-lemus96/fs-nerf) has no FFI layer: its "operator API" for
+ * this path is a handful of Python call sites.  Each entry point below names
+ * the reference interface it replaces (file:line relative to the reference
+ * repo).  The Python mirror of those interfaces (fsnerf_b200/render/rendering.py,
+ * core/models.py, utils/utilities.py) binds this library with ctypes; see
+ * INTEGRATION.md for the stub a reference maintainer would add.
+ *
+ * Conventions: every function returns 0 on success or a negative code
+ * (FSNERF_ERR_*); the message is available from fsnerf_last_error().  The
+ * library never allocates caller-visible memory: all pointers are DEVICE
+ * pointers owned by the caller (contiguous, fp32 unless stated), sizes are
+ * explicit, work is enqueued on `stream` (a cudaStream_t passed as void*).
+ * There is no CPU fallback: without an sm_100 device every compute call fails.
+ */
+#ifndef FSNERF_B200_H
+#define FSNERF_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSNERF_OK 0
+#define FSNERF_ERR_ARG -1
+#define FSNERF_ERR_CUDA -2
+#define FSNERF_ERR_UNSUPPORTED -3
+
+/* compositing flags (default 0 == nerfacc.volrend.rendering semantics as
+ * called at src/render/rendering.py:89-96; the others are the canonical
+ * raw2outputs switches of SURVEY.md Appendix B3) */
+#define FSNERF_COMP_SIGMA_RELU 1     /* sigma = relu(raw sigma)                        */
+#define FSNERF_COMP_DEPTH_UNNORM 2   /* depth = sum w*t (no division by opacity)        */
+#define FSNERF_COMP_PRODUCT_TRANS 4  /* T_i = prod_{j<i}(1-alpha_j+1e-10)               */
+
+int fsnerf_version(void);
+const char* fsnerf_last_error(void);
+/* 0 if device `dev` can run the kernels (compute capability 10.x) */
+int fsnerf_device_ok(int dev);
+
+/* ---- (1) rays --------------------------------------------------------- */
+/* Replaces utils.utilities.get_rays (src/utils/utilities.py:36-82) + the NDC
+ * warp utils.utilities.to_ndc (:84-120) + the per-item ray-table fetch of
+ * LLFFDataset.__getitem__ (src/nerfdata/datasets/llff.py:92-105).
+ * Global pixel id p = view*H*W + h*W + w.  pixel_ids==NULL -> p = first_id+i.
+ * poses: [n_views, pose_rows(3|4), 4].  images (optional): [n_views,H,W,3]
+ * -> rgb_gt[R,3].  sx = -1/(W/(2f)), sy = -1/(H/(2f)) are only read if ndc. */
+int fsnerf_gen_rays(const float* poses, int n_views, int pose_rows, int H, int W, float focal,
+                    const int64_t* pixel_ids, int64_t first_id, int64_t n_rays, int ndc,
+                    float ndc_near, float ndc_sx, float ndc_sy, const float* images, float* rays_o,
+                    float* rays_d, float* rgb_gt, void* stream);
+/* utils.utilities.to_ndc on existing rays (src/utils/utilities.py:84-120) */
+int fsnerf_to_ndc(const float* rays_o, const float* rays_d, int64_t n_rays, float near, float sx,
+                  float sy, float* ndc_o, float* ndc_d, void* stream);
+
+/* Stands in for estimator.sampling (src/render/rendering.py:66-74), replaced
+ * per BASELINE.json north_star by stratified sampling.
+ * u: [R,S] uniforms in [0,1) or NULL (deterministic).  Outputs [R,S]:
+ * t_starts = sorted points z, t_ends = [z[1:], far]. */
+int fsnerf_sample_stratified(int64_t n_rays, int n_samples, float near, float far, const float* u,
+                             float* t_starts, float* t_ends, void* stream);
+/* Hierarchical inverse-CDF resampling (warp-tree CDF order).
+ * z_coarse,w_coarse [R,Sc]; u [R,Sf] or NULL.  Outputs: samples [R,Sf],
+ * inds [R,Sf] int32 (searchsorted right), perm [R,Sc+Sf] int32 (stable sort
+ * permutation of cat(z_coarse,samples)), t_starts/t_ends [R,Sc+Sf].
+ * samples/inds/perm may be NULL. */
+int fsnerf_sample_pdf(int64_t n_rays, int n_coarse, int n_fine, const float* z_coarse,
+                      const float* w_coarse, const float* u, float far, float* samples,
+                      int32_t* inds, int32_t* perm, float* t_starts, float* t_ends, void* stream);
+
+/* ---- (4) compositing -------------------------------------------------- */
+/* Replaces nerfacc.volrend.rendering as called at src/render/rendering.py:89-96
+ * on a dense layout (S samples per ray).  raw [R,S,4]=(rgb,sigma).
+ * delta_scale [R] or NULL; bkgd [3] or NULL.  Outputs rgb[R,3], opacity[R],
+ * depth[R], weights[R,S]; alphas/trans [R,S] optional (NULL to skip). */
+int fsnerf_composite_forward(int64_t n_rays, int n_samples, const float* raw, const float* t_starts,
+                             const float* t_ends, const float* delta_scale, const float* bkgd,
+                             int flags, float* rgb, float* opacity, float* depth, float* weights,
+                             float* alphas, float* trans, void* stream);
+/* Backward of the above (the autograd edge of loss.backward(),
+ * src/run-nerf.py:282).  d_weights [R,S] or NULL.  Outputs d_raw [R,S,4];
+ * d_bkgd [3] (accumulated with atomics, may be NULL). */
+int fsnerf_composite_backward(int64_t n_rays, int n_samples, const float* raw,
+                              const float* t_starts, const float* t_ends, const float* delta_scale,
+                              const float* bkgd, int flags, const float* d_rgb,
+                              const float* d_opacity, const float* d_depth, const float* d_weights,
+                              float* d_raw, float* d_bkgd, void* stream);
+
+/* ---- (2)+(3) NeRF MLP -------------------------------------------------- */
+/* Architecture of core.models.NeRF (src/core/models.py:57-109). */
+typedef struct fsnerf_net_cfg {
+  int n_layers;    /* hidden layers before the bottleneck (8)              */
+  int d_hidden;    /* 256 (the tcgen05 path supports 256 only)             */
+  int skip_mask;   /* bit i: concat PE(x) after layers[i] (ref skip=[4] -> 16) */
+  int n_freqs_pos; /* 10 -> 63 channels                                    */
+  int n_freqs_dir; /* 4  -> 27 channels                                    */
+  int log_space;   /* 1: f_k = 2^k ; 0: linspace(1, 2^(L-1), L)            */
+} fsnerf_net_cfg;
+
+/* number of fp32 parameters in state-dict order (layers.i.weight, layers.i.bias,
+ * ..., sigma, connection, branch, rgb) */
+int64_t fsnerf_mlp_param_count(const fsnerf_net_cfg* cfg);
+/* bytes of the packed bf16 operand image (forward + transposed blocks) */
+int64_t fsnerf_mlp_packed_bytes(const fsnerf_net_cfg* cfg);
+/* bytes of the activation stash the backward needs for n_samples */
+int64_t fsnerf_mlp_stash_bytes(const fsnerf_net_cfg* cfg, int64_t n_samples);
+/* bytes of scratch the backward needs for n_samples */
+int64_t fsnerf_mlp_bwd_workspace_bytes(const fsnerf_net_cfg* cfg, int64_t n_samples);
+/* fp32 params -> packed bf16 SWIZZLE_128B operand blocks */
+int fsnerf_mlp_pack(const fsnerf_net_cfg* cfg, const float* params, void* packed, void* stream);
+
+/* Replaces NeRF.forward (src/core/models.py:111-143) evaluated in the closures
+ * of render_rays (src/render/rendering.py:58-64,76-84): sample p belongs to ray
+ * p / samples_per_ray, position o + d*(t_starts[p]+t_ends[p])/2, view dir d.
+ * If x != NULL the positions (and dirs, if given) are read from x/dirs [P,3]
+ * instead (plain model(x, dirs) call).  mask_pos [3(1+2Lp)] / mask_dir
+ * [3(1+2Ld)] or NULL (FreeNeRF mask, App. B4).  density_only: out is [P]
+ * sigma (model(x) form) else [P,4] = (rgb, sigma).  stash: NULL for inference,
+ * else fsnerf_mlp_stash_bytes() bytes kept for the backward. */
+int fsnerf_mlp_forward(const fsnerf_net_cfg* cfg, const float* params, const void* packed,
+                       int64_t n_samples, int samples_per_ray, const float* rays_o,
+                       const float* rays_d, const float* t_starts, const float* t_ends,
+                       const float* x, const float* dirs, const float* mask_pos,
+                       const float* mask_dir, int density_only, float* out, void* stash,
+                       void* stream);
+/* Backward of fsnerf_mlp_forward: d_out [P,4] (or [P] if density_only) ->
+ * grads (fp32, same layout as params; ACCUMULATED into, caller zeroes). */
+int fsnerf_mlp_backward(const fsnerf_net_cfg* cfg, const float* params, const void* packed,
+                        int64_t n_samples, const void* stash, const float* out,
+                        const float* d_out, int density_only, float* grads, void* workspace,
+                        void* stream);
+
+/* ---- train-step arithmetic (src/run-nerf.py:216-217,255-258,282-285) ---- */
+/* d_rgb = grad_scale*2*(rgb-gt); loss_sum += sum((rgb-gt)^2) (atomic; caller zeroes) */
+int fsnerf_mse_loss_grad(int64_t n, const float* rgb, const float* gt, float grad_scale,
+                         float* loss_sum, float* d_rgb, void* stream);
+/* torch.optim.Adam (defaults) on a flat buffer; step counts from 1 */
+int fsnerf_adam_step(int64_t n, float* params, const float* grads, float* m, float* v, float lr,
+                     float beta1, float beta2, float eps, int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSNERF_B200_H */

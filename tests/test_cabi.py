@@ -1,0 +1,54 @@
+"""CPU tests: the C-ABI library loads and exports every symbol that
+include/fsnerf_b200.h declares (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "fsnerf_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fsnerf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from fsnerf_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = _lib.load()
+    syms = _header_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes prototype"
+    assert set(_lib.SIGNATURES) == set(syms)
+    assert lib.fsnerf_version() >= 100
+    assert isinstance(lib.fsnerf_last_error(), bytes)
+
+
+def test_host_side_layout_queries():
+    """param count / packed bytes are pure host arithmetic: safe without a GPU."""
+    from fsnerf_b200 import ops
+    cfg = ops.make_cfg()
+    assert ops.mlp_param_count(cfg) == 595844  # reference state dict
+    blocks = ops.mlp_packed_bytes(cfg) // 16384
+    assert blocks == 73 + 68 and ops.mlp_packed_bytes(cfg) % 16384 == 0
+    assert ops.mlp_stash_bytes(cfg, 128) == 640 * 1024
+    assert ops.mlp_stash_bytes(cfg, 129) == 2 * 640 * 1024
+    bad = ops.make_cfg(d_hidden=128)
+    from fsnerf_b200._lib import FsnerfError
+    with pytest.raises(FsnerfError, match="d_hidden must be 256"):
+        ops.mlp_param_count(bad)
+
+
+def test_no_cpu_fallback():
+    import torch
+    from fsnerf_b200 import ops
+    from fsnerf_b200._lib import FsnerfError
+    with pytest.raises(FsnerfError, match="CUDA tensor"):
+        ops.composite_forward(torch.zeros(2, 4, 4), torch.zeros(2, 4), torch.ones(2, 4))
