@@ -37,6 +37,7 @@ SIGNATURES = {
     "fsnerf_composite_forward": (_i, [_l, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
     "fsnerf_composite_backward": (_i, [_l, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
     "fsnerf_mlp_param_count": (_l, [C.POINTER(NetCfg)]),
+    "fsnerf_mlp_param_layout": (_i, [C.POINTER(NetCfg), C.POINTER(_l), C.POINTER(_l), _i]),
     "fsnerf_mlp_packed_bytes": (_l, [C.POINTER(NetCfg)]),
     "fsnerf_mlp_stash_bytes": (_l, [C.POINTER(NetCfg), _l]),
     "fsnerf_mlp_bwd_workspace_bytes": (_l, [C.POINTER(NetCfg), _l]),

@@ -253,6 +253,7 @@ extern "C" int fsnerf_composite_forward(int64_t n_rays, int n_samples, const flo
                                         const float* delta_scale, const float* bkgd, int flags,
                                         float* rgb, float* opacity, float* depth, float* weights,
                                         float* alphas, float* trans, void* stream) {
+  if (n_rays == 0) return FSNERF_OK;
   FS_REQUIRE(raw && t_starts && t_ends && rgb && opacity && depth && weights,
              "composite_forward: null pointer");
   FS_REQUIRE(n_samples >= 1 && n_rays >= 0, "composite_forward: bad sizes");
@@ -279,6 +280,7 @@ extern "C" int fsnerf_composite_backward(int64_t n_rays, int n_samples, const fl
                                          const float* d_rgb, const float* d_opacity,
                                          const float* d_depth, const float* d_weights, float* d_raw,
                                          float* d_bkgd, void* stream) {
+  if (n_rays == 0) return FSNERF_OK;
   FS_REQUIRE(raw && t_starts && t_ends && d_rgb && d_raw, "composite_backward: null pointer");
   FS_REQUIRE(n_samples >= 1 && n_samples <= 512, "composite_backward: n_samples must be in [1,512]");
   FS_REQUIRE(((reinterpret_cast<uintptr_t>(raw) | reinterpret_cast<uintptr_t>(d_raw)) & 15) == 0,

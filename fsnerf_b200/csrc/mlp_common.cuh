@@ -1,7 +1,8 @@
 // Host/device shared description of the fused NeRF MLP "program".
 //
 // Data layout in HBM:
-//  * params   fp32, flat, reference state-dict order (src/core/models.py:96-108).
+//  * params   fp32, flat, reference state-dict order (src/core/models.py:96-108),
+//             each tensor starting on a 16 B boundary (fsnerf_mlp_param_layout).
 //  * packed   bf16 operand image: a sequence of 16 KB blocks, each a
 //             [128 rows x 64 K] K-major SWIZZLE_128B tile ready to be the B
 //             operand of tcgen05.mma after ONE bulk copy.  Forward blocks are
@@ -56,7 +57,10 @@ struct MlpProgram {
   int sigma_w_off, sigma_b_off, rgb_w_off, rgb_b_off;
   int stash_aux_pos_off, stash_aux_dir_off;  // byte offsets in the tile record
   int stash_tile_bytes;
-  int64_t n_params;
+  int64_t n_params;      // flat fp32 length incl. alignment padding
+  int n_tensors;         // state-dict tensors (2 per Linear)
+  int64_t tensor_off[2 * kMaxGemm + 8];
+  int64_t tensor_numel[2 * kMaxGemm + 8];
   int64_t packed_bytes;
   GemmLayer layer[kMaxGemm];
 };

@@ -327,8 +327,9 @@ extern "C" int fsnerf_mlp_forward(const fsnerf_net_cfg* cfg, const float* params
   static MlpProgram P;
   int rc = build_program(cfg, &P);
   if (rc != FSNERF_OK) return rc;
-  FS_REQUIRE(params && packed && out, "mlp_forward: null pointer");
   FS_REQUIRE(n_samples >= 0, "mlp_forward: negative n_samples");
+  if (n_samples == 0) return FSNERF_OK;
+  FS_REQUIRE(params && packed && out, "mlp_forward: null pointer");
   if (x) {
     FS_REQUIRE(density_only || dirs, "mlp_forward: dirs required unless density_only");
   } else {

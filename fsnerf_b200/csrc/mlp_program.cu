@@ -39,6 +39,17 @@ int build_program(const fsnerf_net_cfg* cfg, MlpProgram* P) {
     }
   }
   int64_t off = 0;
+  auto al4 = [](int64_t v) { return (v + 3) & ~(int64_t)3; };
+  int n_t = 0;
+  auto tensor = [&](int64_t numel) {  // next tensor in state-dict order, 16 B aligned
+    off = al4(off);
+    int64_t o = off;
+    P->tensor_off[n_t] = o;
+    P->tensor_numel[n_t] = numel;
+    ++n_t;
+    off += numel;
+    return (int)o;
+  };
   int blk = 0;
   int stash = 0;
   P->stash_aux_pos_off = stash;
@@ -53,22 +64,20 @@ int build_program(const fsnerf_net_cfg* cfg, MlpProgram* P) {
     L.n_halves = H / 128;
     L.epi = (i == n - 1) ? EPI_RELU_SIGMA : EPI_RELU;
     L.ld = first ? P->d_pos : (skip_in ? H + P->d_pos : H);
-    L.w_off = (int)off;
-    off += (int64_t)H * L.ld;
-    L.bias_off = (int)off;
-    off += H;
+    L.w_off = tensor((int64_t)H * L.ld);
+    L.bias_off = tensor(H);
     L.first_block = blk;
     blk += (L.n_act_chunks + L.use_aux) * L.n_halves;
     L.stash_off = stash;
     stash += (H / 64) * kChunkBytes;
   }
-  P->sigma_w_off = (int)off; off += H;
-  P->sigma_b_off = (int)off; off += 1;
+  P->sigma_w_off = tensor(H);
+  P->sigma_b_off = tensor(1);
   P->n_blocks_fwd_density = blk;
   {  // connection
     GemmLayer& L = P->layer[g++];
     L.n_act_chunks = H / 64; L.use_aux = 0; L.n_halves = H / 128; L.epi = EPI_CONN;
-    L.ld = H; L.w_off = (int)off; off += (int64_t)H * H; L.bias_off = (int)off; off += H;
+    L.ld = H; L.w_off = tensor((int64_t)H * H); L.bias_off = tensor(H);
     L.first_block = blk; blk += L.n_act_chunks * L.n_halves;
     L.stash_off = stash; stash += (H / 64) * kChunkBytes;
   }
@@ -77,13 +86,15 @@ int build_program(const fsnerf_net_cfg* cfg, MlpProgram* P) {
   {  // branch
     GemmLayer& L = P->layer[g++];
     L.n_act_chunks = H / 64; L.use_aux = 1; L.n_halves = (H / 2) / 128; L.epi = EPI_BRANCH;
-    L.ld = H + P->d_dir; L.w_off = (int)off; off += (int64_t)(H / 2) * L.ld;
-    L.bias_off = (int)off; off += H / 2;
+    L.ld = H + P->d_dir; L.w_off = tensor((int64_t)(H / 2) * L.ld);
+    L.bias_off = tensor(H / 2);
     L.first_block = blk; blk += (L.n_act_chunks + 1) * L.n_halves;
     L.stash_off = stash; stash += ((H / 2) / 64) * kChunkBytes;
   }
-  P->rgb_w_off = (int)off; off += 3 * (H / 2);
-  P->rgb_b_off = (int)off; off += 3;
+  P->rgb_w_off = tensor(3 * (H / 2));
+  P->rgb_b_off = tensor(3);
+  off = al4(off);
+  P->n_tensors = n_t;
   P->n_gemm = g;
   P->n_blocks_fwd = blk;
   P->n_params = off;
@@ -149,6 +160,19 @@ extern "C" int64_t fsnerf_mlp_param_count(const fsnerf_net_cfg* cfg) {
   MlpProgram P;
   if (build_program(cfg, &P) != FSNERF_OK) return -1;
   return P.n_params;
+}
+extern "C" int fsnerf_mlp_param_layout(const fsnerf_net_cfg* cfg, int64_t* offsets, int64_t* numels,
+                                       int max_tensors) {
+  MlpProgram P;
+  int rc = build_program(cfg, &P);
+  if (rc != FSNERF_OK) return rc;
+  FS_REQUIRE(offsets && numels && max_tensors >= P.n_tensors, "mlp_param_layout: need room for %d tensors",
+             P.n_tensors);
+  for (int i = 0; i < P.n_tensors; ++i) {
+    offsets[i] = P.tensor_off[i];
+    numels[i] = P.tensor_numel[i];
+  }
+  return P.n_tensors;
 }
 extern "C" int64_t fsnerf_mlp_packed_bytes(const fsnerf_net_cfg* cfg) {
   MlpProgram P;

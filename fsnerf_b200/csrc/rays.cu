@@ -221,6 +221,7 @@ extern "C" int fsnerf_gen_rays(const float* poses, int n_views, int pose_rows, i
                                int64_t n_rays, int ndc, float ndc_near, float ndc_sx, float ndc_sy,
                                const float* images, float* rays_o, float* rays_d, float* rgb_gt,
                                void* stream) {
+  if (n_rays == 0) return FSNERF_OK;
   FS_REQUIRE(poses && rays_o && rays_d, "gen_rays: null pointer");
   FS_REQUIRE(pose_rows == 3 || pose_rows == 4, "gen_rays: pose_rows must be 3 or 4");
   FS_REQUIRE(H > 0 && W > 0 && n_views > 0 && n_rays >= 0, "gen_rays: bad sizes");
@@ -235,8 +236,8 @@ extern "C" int fsnerf_gen_rays(const float* poses, int n_views, int pose_rows, i
 
 extern "C" int fsnerf_to_ndc(const float* rays_o, const float* rays_d, int64_t n_rays, float near,
                              float sx, float sy, float* ndc_o, float* ndc_d, void* stream) {
-  FS_REQUIRE(rays_o && rays_d && ndc_o && ndc_d, "to_ndc: null pointer");
   if (n_rays == 0) return FSNERF_OK;
+  FS_REQUIRE(rays_o && rays_d && ndc_o && ndc_d, "to_ndc: null pointer");
   int threads = 256;
   int64_t blocks = (n_rays + threads - 1) / threads;
   to_ndc_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(rays_o, rays_d, n_rays,
@@ -247,9 +248,9 @@ extern "C" int fsnerf_to_ndc(const float* rays_o, const float* rays_d, int64_t n
 extern "C" int fsnerf_sample_stratified(int64_t n_rays, int n_samples, float near, float far,
                                         const float* u, float* t_starts, float* t_ends,
                                         void* stream) {
-  FS_REQUIRE(t_starts && t_ends, "sample_stratified: null output");
   FS_REQUIRE(n_samples >= 1 && n_rays >= 0, "sample_stratified: bad sizes");
   if (n_rays == 0) return FSNERF_OK;
+  FS_REQUIRE(t_starts && t_ends, "sample_stratified: null output");
   int64_t n = n_rays * n_samples;
   int threads = 256;
   stratified_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
@@ -261,6 +262,7 @@ extern "C" int fsnerf_sample_pdf(int64_t n_rays, int n_coarse, int n_fine, const
                                  const float* w_coarse, const float* u, float far, float* samples,
                                  int32_t* inds, int32_t* perm, float* t_starts, float* t_ends,
                                  void* stream) {
+  if (n_rays == 0) return FSNERF_OK;
   FS_REQUIRE(z_coarse && w_coarse && t_starts && t_ends, "sample_pdf: null pointer");
   FS_REQUIRE(n_coarse >= 3 && n_coarse - 2 <= 32 * kPdfMaxE, "sample_pdf: n_coarse must be in [3,258]");
   FS_REQUIRE(n_fine >= 1 && n_fine <= 1024, "sample_pdf: n_fine must be in [1,1024]");

@@ -142,6 +142,37 @@ def mlp_param_count(cfg):
     return n
 
 
+def mlp_param_layout(cfg):
+    """-> list of (offset, numel) in floats, one per state-dict tensor (reference order)."""
+    off = (C.c_int64 * 64)()
+    num = (C.c_int64 * 64)()
+    n = _lib.load().fsnerf_mlp_param_layout(C.byref(cfg), off, num, 64)
+    if n < 0:
+        check(n, "fsnerf_mlp_param_layout")
+    return [(off[i], num[i]) for i in range(n)]
+
+
+def state_dict_names(cfg):
+    """the reference's state_dict() keys, in order (src/core/models.py:96-108)"""
+    mods = [f"layers.{i}" for i in range(cfg.n_layers)] + ["sigma", "connection", "branch", "rgb"]
+    return [f"{m}.{k}" for m in mods for k in ("weight", "bias")]
+
+
+def flatten_state_dict(cfg, sd, device):
+    """state dict (reference keys) -> flat fp32 parameter buffer on `device`."""
+    layout = mlp_param_layout(cfg)
+    names = state_dict_names(cfg)
+    if len(names) != len(layout) or set(names) != set(sd.keys()):
+        raise _lib.FsnerfError("state dict keys do not match the network configuration")
+    flat = torch.zeros(mlp_param_count(cfg), device=device)
+    for (o, n), name in zip(layout, names):
+        v = sd[name]
+        if v.numel() != n:
+            raise _lib.FsnerfError(f"state dict tensor {name}: {v.numel()} elements, expected {n}")
+        flat[o:o + n] = v.detach().reshape(-1).to(device=device, dtype=torch.float32)
+    return flat
+
+
 def mlp_packed_bytes(cfg):
     n = _lib.load().fsnerf_mlp_packed_bytes(C.byref(cfg))
     if n < 0:

@@ -98,9 +98,15 @@ typedef struct fsnerf_net_cfg {
   int log_space;   /* 1: f_k = 2^k ; 0: linspace(1, 2^(L-1), L)            */
 } fsnerf_net_cfg;
 
-/* number of fp32 parameters in state-dict order (layers.i.weight, layers.i.bias,
- * ..., sigma, connection, branch, rgb) */
+/* Flat fp32 parameter buffer: tensors in the reference's state-dict order
+ * (layers.i.weight, layers.i.bias, ..., sigma, connection, branch, rgb;
+ * src/core/models.py:96-108), each starting on a 16-byte boundary.
+ * fsnerf_mlp_param_count = length of that buffer in floats (incl. padding);
+ * fsnerf_mlp_param_layout fills offsets/numels (floats) of every tensor and
+ * returns the tensor count (24 for the default net) or a negative code. */
 int64_t fsnerf_mlp_param_count(const fsnerf_net_cfg* cfg);
+int fsnerf_mlp_param_layout(const fsnerf_net_cfg* cfg, int64_t* offsets, int64_t* numels,
+                            int max_tensors);
 /* bytes of the packed bf16 operand image (forward + transposed blocks) */
 int64_t fsnerf_mlp_packed_bytes(const fsnerf_net_cfg* cfg);
 /* bytes of the activation stash the backward needs for n_samples */

@@ -37,7 +37,9 @@ def init_state_dict(n_layers=8, d_hidden=256, skip=(4,), n_freqs=10,
         linear("connection", d_hidden, d_hidden)
         linear("branch", d_hidden + d_de, d_hidden // 2)
         linear("rgb", d_hidden // 2, 3)
-    return sd
+    # hand back in state_dict() key order (module registration order)
+    names = [f"layers.{i}" for i in range(n_layers)] + ["sigma", "connection", "branch", "rgb"]
+    return {f"{n}.{k}": sd[f"{n}.{k}"] for n in names for k in ("weight", "bias")}
 
 
 def nerf_forward(sd, x, dirs=None, n_layers=8, skip=(4,), n_freqs=10,

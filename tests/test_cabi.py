@@ -35,7 +35,10 @@ def test_host_side_layout_queries():
     """param count / packed bytes are pure host arithmetic: safe without a GPU."""
     from fsnerf_b200 import ops
     cfg = ops.make_cfg()
-    assert ops.mlp_param_count(cfg) == 595844  # reference state dict (SURVEY.md §8 a5)
+    layout = ops.mlp_param_layout(cfg)
+    assert len(layout) == 24 and sum(n for _, n in layout) == 595844  # reference state dict (SURVEY.md §8 a5)
+    assert all(o % 4 == 0 for o, _ in layout) and ops.mlp_param_count(cfg) % 4 == 0
+    assert ops.mlp_param_count(cfg) >= 595844
     blocks = ops.mlp_packed_bytes(cfg) // 16384
     assert blocks == 73 + 68 and ops.mlp_packed_bytes(cfg) % 16384 == 0
     assert ops.mlp_stash_bytes(cfg, 128) == 640 * 1024
@@ -52,3 +55,15 @@ def test_no_cpu_fallback():
     from fsnerf_b200._lib import FsnerfError
     with pytest.raises(FsnerfError, match="CUDA tensor"):
         ops.composite_forward(torch.zeros(2, 4, 4), torch.zeros(2, 4), torch.ones(2, 4))
+
+
+def test_flatten_state_dict_layout():
+    import torch
+    from fsnerf_b200 import ops
+    from oracle import mlp as omlp
+    cfg = ops.make_cfg()
+    sd = omlp.init_state_dict()
+    assert list(sd.keys()) == ops.state_dict_names(cfg)
+    flat = ops.flatten_state_dict(cfg, sd, "cpu")
+    for (o, n), name in zip(ops.mlp_param_layout(cfg), ops.state_dict_names(cfg)):
+        assert torch.equal(flat[o:o + n], sd[name].reshape(-1))
