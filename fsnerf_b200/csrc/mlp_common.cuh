@@ -43,6 +43,7 @@ struct GemmLayer {
   int bwd_first_block;  // first dgrad block (W^T) of this layer, -1 if no dgrad needed
   int bwd_n_halves;     // dgrad output width / 128 (2)
   int bwd_n_chunks;     // dgrad K chunks = N_out / 64
+  int dstash_off;       // byte offset of d(pre-activation) image in a tile's backward record
 };
 
 struct MlpProgram {
@@ -57,6 +58,7 @@ struct MlpProgram {
   int sigma_w_off, sigma_b_off, rgb_w_off, rgb_b_off;
   int stash_aux_pos_off, stash_aux_dir_off;  // byte offsets in the tile record
   int stash_tile_bytes;
+  int dstash_tile_bytes;  // backward workspace record per tile (dpre images of every GEMM layer)
   int64_t n_params;      // flat fp32 length incl. alignment padding
   int n_tensors;         // state-dict tensors (2 per Linear)
   int64_t tensor_off[2 * kMaxGemm + 8];

@@ -109,6 +109,12 @@ int build_program(const fsnerf_net_cfg* cfg, MlpProgram* P) {
     blk += L.bwd_n_halves * L.bwd_n_chunks;
   }
   P->layer[0].bwd_first_block = -1;
+  int dst = 0;
+  for (int gi = 0; gi < P->n_gemm; ++gi) {
+    P->layer[gi].dstash_off = dst;
+    dst += (P->layer[gi].n_halves * 128 / 64) * kChunkBytes;
+  }
+  P->dstash_tile_bytes = dst;
   P->n_blocks_bwd = blk - P->n_blocks_fwd;
   P->packed_bytes = (int64_t)blk * kBlockBytes;
   return FSNERF_OK;

@@ -71,3 +71,54 @@ def nerf_forward(sd, x, dirs=None, n_layers=8, skip=(4,), n_freqs=10,
     h = F.relu(F.linear(h, sd["branch.weight"], sd["branch.bias"]))
     rgb = torch.sigmoid(F.linear(h, sd["rgb.weight"], sd["rgb.bias"]))
     return torch.cat([rgb, sigma], -1)
+
+
+# --------------------------------------------------------------------------
+# bf16-operand emulation of the CUDA path (tests only).  Same math as
+# nerf_forward but rounded to bfloat16 exactly where the kernels round:
+# encodings, every GEMM input activation (the stash images), the weights fed to
+# the tensor cores, and d(pre-activation) in the backward.  Accumulation stays
+# fp32.  This isolates kernel bugs from the (expected) bf16-vs-fp32 gap.
+class _RoundGradBf16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+def _r(x):
+    """round to bf16, straight-through gradient"""
+    return x + (x.bfloat16().float() - x).detach()
+
+
+def nerf_forward_bf16emu(sd, x, dirs, n_layers=8, skip=(4,), n_freqs=10, n_freqs_dir=4,
+                         log_space=True, mask_pos=None, mask_dir=None):
+    def lin(h_r, name):
+        pre = F.linear(h_r, _r(sd[f"{name}.weight"]), sd[f"{name}.bias"])
+        return _RoundGradBf16.apply(pre)
+
+    x_in = positional_encoding(x, n_freqs, log_space)
+    if mask_pos is not None:
+        x_in = x_in * mask_pos
+    x_in = x_in.bfloat16().float()
+    h_r = x_in
+    h = None
+    for i in range(n_layers):
+        h = F.relu(lin(h_r, f"layers.{i}"))
+        h_r = _r(h)
+        # kernel's ReLU mask is (bf16(h) != 0): kill the gradient where rounding flushed to 0
+        h_r = h_r * (h_r.detach() != 0)
+        if i in skip:
+            h_r = torch.cat([h_r, x_in], -1)
+    sigma = F.linear(h, sd["sigma.weight"], sd["sigma.bias"])  # fp32 head on CUDA cores
+    c_r = _r(lin(h_r, "connection"))
+    d_in = positional_encoding(dirs, n_freqs_dir, log_space)
+    if mask_dir is not None:
+        d_in = d_in * mask_dir
+    d_in = d_in.bfloat16().float()
+    hb = F.relu(lin(torch.cat([c_r, d_in], -1), "branch"))
+    rgb = torch.sigmoid(F.linear(hb, sd["rgb.weight"], sd["rgb.bias"]))
+    return torch.cat([rgb, sigma], -1)
