@@ -137,7 +137,7 @@ sample_pdf_kernel(int64_t n_rays, int Sc, int Sf, const float* __restrict__ z_co
   for (int e = 0; e < kPdfMaxE; ++e) {
     if (e < E) {
       int j = lane * E + e;
-      wp[e] = (j < nw) ? __fadd_rn(wc[j + 1], 1e-5f) : 0.0f;
+      wp[e] = (j < nw) ? __fadd_rn(fmaxf(wc[j + 1], 0.0f), 1e-5f) : 0.0f;
       s = (e == 0) ? wp[0] : __fadd_rn(s, wp[e]);
     }
   }

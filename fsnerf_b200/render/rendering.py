@@ -1,0 +1,230 @@
+"""Drop-in for the reference's ``render.rendering`` entry points
+(/root/reference/src/render/rendering.py:25-248): ``render_rays``,
+``render_frame``, ``render_path`` with the same signatures and return
+structures.  Sampling (stratified + hierarchical sample_pdf, per
+BASELINE.json north_star, standing in for nerfacc's occupancy-grid sampler),
+the MLP and the compositor run in the CUDA kernels of libfsnerf_b200.so.
+"""
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+from torch import nn, Tensor
+
+from .. import ops
+from .._lib import FsnerfError
+from ..utils import utilities as U
+
+to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)  # noqa: E731  (reference :22)
+
+
+class _RenderFunction(torch.autograd.Function):
+    """rays + intervals -> MLP (fused encode + tcgen05 MLP) -> compositing.
+    One autograd node so that loss.backward() (src/run-nerf.py:282) reaches the
+    model parameters and the background colour."""
+
+    @staticmethod
+    def forward(ctx, model, rays_o, rays_d, ts, te, bkgd, flags, need_grad, *params):
+        R, S = ts.shape
+        packed = model._refresh_packed()
+        stash = None
+        if need_grad:
+            stash = torch.empty(ops.mlp_stash_bytes(model.cfg, R * S), dtype=torch.uint8, device=ts.device)
+        raw = ops.mlp_forward(model.cfg, model._flat, packed, rays_o=rays_o, rays_d=rays_d,
+                              t_starts=ts, t_ends=te, mask_pos=model.mask_pos,
+                              mask_dir=model.mask_dir, stash=stash)
+        bk = None if bkgd is None else bkgd.detach()
+        rgb, op, dp, w, al, tr = ops.composite_forward(raw.view(R, S, 4), ts, te, bkgd=bk, flags=flags,
+                                                       extras=True)
+        ctx.model, ctx.packed, ctx.stash, ctx.flags, ctx.shape = model, packed, stash, flags, (R, S)
+        ctx.has_bkgd = bkgd is not None
+        ctx.save_for_backward(raw, ts, te, bk if bk is not None else raw.new_empty(0))
+        ctx.mark_non_differentiable(raw, al, tr)
+        return rgb, op, dp, w, raw, al, tr
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_op, d_dp, d_w, _d_raw, _d_al, _d_tr):
+        model = ctx.model
+        raw, ts, te, bk = ctx.saved_tensors
+        R, S = ctx.shape
+        bk = bk if ctx.has_bkgd else None
+        zero = lambda g, shape: torch.zeros(shape, device=raw.device) if g is None else g.contiguous()  # noqa: E731
+        d_raw, d_bk = ops.composite_backward(raw.view(R, S, 4), ts, te, zero(d_rgb, (R, 3)),
+                                             zero(d_op, (R, 1)), zero(d_dp, (R, 1)),
+                                             None if d_w is None else d_w.contiguous(), bkgd=bk,
+                                             flags=ctx.flags, want_d_bkgd=ctx.has_bkgd)
+        grads = torch.zeros_like(model._flat)
+        ws = torch.empty(ops.mlp_bwd_workspace_bytes(model.cfg, R * S), dtype=torch.uint8, device=raw.device)
+        ops.mlp_backward(model.cfg, model._flat, ctx.packed, R * S, ctx.stash, raw, d_raw.view(-1, 4), grads, ws)
+        views = [grads[o:o + n].view(p.shape) for (o, n), p in zip(model._layout, model._param_list())]
+        return (None, None, None, None, None, d_bk, None, None, *views)
+
+
+def volume_render(model, rays_o, rays_d, t_starts, t_ends, render_bkgd=None, flags=0):
+    """Stands in for ``nerfacc.volrend.rendering`` + the ``rgb_sigma_fn`` closure
+    (reference :76-96) on a dense [R,S] sample layout.
+    -> (rgb[R,3], opacity[R,1], depth[R,1], weights[R,S], raw[R*S,4], alphas[R,S], trans[R,S])"""
+    params = model._param_list()
+    # (grad mode is always off inside Function.forward, so decide here)
+    need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or (
+        render_bkgd is not None and render_bkgd.requires_grad))
+    return _RenderFunction.apply(model, rays_o, rays_d, t_starts, t_ends, render_bkgd, flags, need_grad,
+                                 *params)
+
+
+class HierarchicalEstimator(nn.Module):
+    """Estimator-shaped object (the reference builds an
+    ``OccGridEstimator(roi_aabb, resolution, levels)``, src/run-nerf.py:96-98, and
+    calls ``.sampling`` / ``.update_every_n_steps`` / ``.train`` / ``.eval`` /
+    ``.to``).  Sampling is stratified in [near, far] (``n_coarse`` points) and,
+    when ``n_fine > 0``, refined by sample_pdf over the weights of a coarse pass
+    through ``proposal_model`` (the canonical coarse network)."""
+
+    def __init__(self, roi_aabb=None, resolution: int = 128, levels: int = 1, *, near: float = 2.0,
+                 far: float = 6.0, n_coarse: int = 64, n_fine: int = 0,
+                 proposal_model: Optional[nn.Module] = None) -> None:
+        super().__init__()
+        self.roi_aabb, self.resolution, self.levels = roi_aabb, resolution, levels
+        self.near, self.far = float(near), float(far)
+        self.n_coarse, self.n_fine = int(n_coarse), int(n_fine)
+        if self.n_fine > 0 and proposal_model is None:
+            raise FsnerfError("HierarchicalEstimator: n_fine > 0 needs a proposal (coarse) model")
+        self.proposal_model = proposal_model
+        self._u_strat = self._u_pdf = None
+        self.last = {}
+
+    def set_uniforms(self, u_strat: Optional[Tensor], u_pdf: Optional[Tensor]) -> None:
+        """Explicit uniforms for the next sampling() call (parity tests feed the same
+        ones to the oracle); otherwise torch.rand on the device."""
+        self._u_strat, self._u_pdf = u_strat, u_pdf
+
+    @property
+    def samples_per_ray(self) -> int:
+        return self.n_coarse + self.n_fine
+
+    def sampling(self, rays_o, rays_d, sigma_fn=None, render_step_size=None, stratified=False,
+                 near_plane=None, far_plane=None, white_bkgd=False):
+        """-> packed (ray_indices[N] int64, t_starts[N], t_ends[N]), N = R*S
+        (same triple as OccGridEstimator.sampling, reference :66-74).  The
+        reference passes near_plane=0 / far_plane=1e10 and ignores the dataset
+        bounds (App. C3): bounds come from this object."""
+        R = rays_o.shape[0]
+        dev = rays_o.device
+        us, up = self._u_strat, self._u_pdf
+        self._u_strat = self._u_pdf = None
+        if stratified and us is None:
+            us = torch.rand(R, self.n_coarse, device=dev)
+        ts, te = ops.sample_stratified(R, self.n_coarse, self.near, self.far, us if stratified else None,
+                                       device=dev)
+        self.last = {}
+        if self.n_fine > 0:
+            bk = (torch.ones(3, device=dev) if white_bkgd else None)
+            rgb_c, op_c, dp_c, w_c, *_ = volume_render(self.proposal_model, rays_o, rays_d, ts, te, bk)
+            self.last = dict(rgb_coarse=rgb_c, opacity_coarse=op_c, depth_coarse=dp_c,
+                             weights_coarse=w_c, t_starts_coarse=ts, t_ends_coarse=te)
+            if stratified and up is None:
+                up = torch.rand(R, self.n_fine, device=dev)
+            ts, te, *_ = ops.sample_pdf(ts, w_c.detach(), self.n_fine, self.far,
+                                        up if stratified else None, want_aux=False)
+        S = ts.shape[1]
+        ray_indices = torch.arange(R, device=dev).repeat_interleave(S)
+        self._dense = (ts, te)
+        return ray_indices, ts.reshape(-1), te.reshape(-1)
+
+    def update_every_n_steps(self, step=None, occ_eval_fn=None, occ_thre=None, **kw) -> None:
+        """No occupancy grid on this path: kept so that the
+        reference's train loop (src/run-nerf.py:293-295) runs unchanged."""
+        return None
+
+
+def render_rays(rays_o: Tensor, rays_d: Tensor, estimator, model: nn.Module, train: bool = False,
+                white_bkgd: bool = False, render_step_size: float = 5e-3,
+                device: torch.device = torch.device("cuda")) -> Tuple[Tensor]:
+    """reference: src/render/rendering.py:25-107.
+    -> ((rgb[R,3], opacity[R,1], depth[R,1], extras), ray_indices[N], t_vals[N])
+    extras: weights/alphas/trans/sigmas/rgbs (packed [N]) like nerfacc's, plus
+    rgb_coarse/opacity_coarse/depth_coarse when the estimator is hierarchical."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise FsnerfError("render_rays: fsnerf_b200 has no CPU path; pass a CUDA device")
+    rays_o = rays_o.to(device=device, dtype=torch.float32).contiguous()  # also un-expands stride-0 origins
+    rays_d = rays_d.to(device=device, dtype=torch.float32).contiguous()
+    R = rays_o.shape[0]
+    ray_indices, t_starts, t_ends = estimator.sampling(
+        rays_o, rays_d, sigma_fn=None, render_step_size=render_step_size, stratified=train,
+        near_plane=0.0, far_plane=1e10, white_bkgd=white_bkgd)
+    S = t_starts.numel() // max(R, 1)
+    ts, te = t_starts.view(R, S), t_ends.view(R, S)
+    render_bkgd = white_bkgd * torch.ones((3,), device=device, requires_grad=train)
+    rgb, opacity, depth, weights, raw, alphas, trans = volume_render(model, rays_o, rays_d, ts, te,
+                                                                     render_bkgd)
+    extras = dict(weights=weights.reshape(-1), alphas=alphas.reshape(-1), trans=trans.reshape(-1),
+                  sigmas=raw[:, 3], rgbs=raw[:, :3])
+    extras.update(getattr(estimator, "last", {}))
+    t_vals = (t_starts + t_ends) / 2.0
+    return (rgb, opacity, depth, extras), ray_indices, t_vals
+
+
+def render_frame(hwf, near: float, far: float, pose: Tensor, chunksize: int, estimator, model: nn.Module,
+                 train: bool = False, ndc: bool = False, white_bkgd: bool = False,
+                 render_step_size: float = 5e-3, device: torch.device = torch.device("cuda"),
+                 compat_positional_bug: bool = False, pixel_range: Optional[Tuple[int, int]] = None):
+    """reference: src/render/rendering.py:110-177 -> (img[H,W,3], depth[H,W]).
+    The reference passes ``white_bkgd`` positionally into render_rays' ``train``
+    slot (:160-168); that is reproduced only with
+    ``compat_positional_bug=True``.  ``pixel_range=(a,b)`` renders the flattened
+    pixels [a,b) only (multi-GPU pixel partition) and returns flat [b-a,3],[b-a]."""
+    H, W, focal = hwf
+    H, W = int(H), int(W)
+    device = torch.device(device)
+    a, b = (0, H * W) if pixel_range is None else pixel_range
+    pose = pose.to(device=device, dtype=torch.float32)
+    rays_o, rays_d, _ = ops.gen_rays(pose[None].contiguous(), H, W, float(focal), first_id=a, n_rays=b - a,
+                                     ndc=ndc, ndc_near=1.0)
+    img, depth_map = [], []
+    for ro, rd in zip(U.get_chunks(rays_o, chunksize), U.get_chunks(rays_d, chunksize)):
+        if compat_positional_bug:
+            out = render_rays(ro, rd, estimator, model, white_bkgd, render_step_size=render_step_size,
+                              device=device)
+        else:
+            out = render_rays(ro, rd, estimator, model, train=train, white_bkgd=white_bkgd,
+                              render_step_size=render_step_size, device=device)
+        (rgb, _, dpt, _), *_ = out
+        img.append(rgb)
+        depth_map.append(dpt)
+    img = torch.cat(img, dim=0)
+    depth = torch.cat(depth_map, dim=0).clamp(near, far)
+    if pixel_range is not None:
+        return img, depth.reshape(-1)
+    return img.reshape(H, W, 3), depth.reshape(H, W)
+
+
+def render_path(render_poses: Tensor, hwf, near: float, far: float, chunksize: int, model: nn.Module,
+                estimator, ndc: bool = False, train: bool = False, white_bkgd: bool = False,
+                render_step_size: float = 5e-3, device: torch.device = torch.device("cuda"),
+                rank: int = 0, world_size: int = 1):
+    """reference: src/render/rendering.py:180-248 -> (frames[F,H,W,3], d_frames[F,H,W])
+    numpy fp32.  With world_size > 1 the flattened F*H*W pixel range is split in
+    contiguous slices, rank r renders slice r and returns only its flat slice
+    (frames[n_r,3], d_frames[n_r], (start, stop)): no collective is needed."""
+    H, W, _ = hwf
+    H, W = int(H), int(W)
+    F = len(render_poses)
+    total = F * H * W
+    start, stop = (total * rank) // world_size, (total * (rank + 1)) // world_size
+    frames, d_frames = [], []
+    with torch.no_grad():
+        for i, pose in enumerate(render_poses):
+            a, b = max(start, i * H * W), min(stop, (i + 1) * H * W)
+            if a >= b:
+                continue
+            rng = None if (a == i * H * W and b == (i + 1) * H * W) else (a - i * H * W, b - i * H * W)
+            rgb, depth = render_frame(hwf, near, far, pose, chunksize, estimator, model, train=train, ndc=ndc,
+                                      white_bkgd=white_bkgd, render_step_size=render_step_size,
+                                      device=device, pixel_range=rng)
+            frames.append(rgb.reshape(-1, 3).detach().cpu().numpy())
+            d_frames.append(depth.reshape(-1).detach().cpu().numpy())
+    if world_size == 1:
+        return (np.stack([f.reshape(H, W, 3) for f in frames], 0),
+                np.stack([d.reshape(H, W) for d in d_frames], 0))
+    return np.concatenate(frames, 0), np.concatenate(d_frames, 0), (start, stop)

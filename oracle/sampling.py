@@ -106,7 +106,9 @@ def sample_pdf(z_coarse, w_coarse, n_fine, far, u=None):
     w_coarse = np.asarray(w_coarse, f32)
     R, Sc = z_coarse.shape
     bins = (f32(0.5) * (z_coarse[:, 1:] + z_coarse[:, :-1])).astype(f32)  # [R,Sc-1]
-    wp = (w_coarse[:, 1:-1] + EPS_W).astype(f32)                          # [R,Sc-2]
+    # weights are clamped at 0: the reference's raw (un-activated) sigma can make
+    # compositing weights negative, which is not a density a CDF can be built from
+    wp = (np.maximum(w_coarse[:, 1:-1], f32(0.0)) + EPS_W).astype(f32)   # [R,Sc-2]
     cdf = _warp_tree_cdf(wp)                                              # [R,Sc-1]
     nb = Sc - 1
     if u is None:
