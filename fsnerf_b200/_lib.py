@@ -46,6 +46,9 @@ SIGNATURES = {
                                 _i, _p, _p, _p]),
     "fsnerf_mlp_backward": (_i, [C.POINTER(NetCfg), _p, _p, _l, _p, _p, _p, _i, _p, _p, _p]),
     "fsnerf_mse_loss_grad": (_i, [_l, _p, _p, _f, _p, _p, _p]),
+    "fsnerf_profile_enable": (_i, [_i]),
+    "fsnerf_profile_read": (_i, [_i, C.c_char_p, C.POINTER(_f), C.POINTER(_i)]),
+    "fsnerf_debug_set_trace": (_i, [_p]),
     "fsnerf_adam_step": (_i, [_l, _p, _p, _p, _p, _f, _f, _f, _f, _i, _p]),
 }
 

@@ -23,6 +23,64 @@ int fsnerf_check_launch(const char* what) {
   return FSNERF_OK;
 }
 
+// ---------------------------------------------------------------- profiling
+#include <string.h>
+#include <vector>
+namespace {
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+}  // namespace
+
+FsProfScope::FsProfScope(const char* name, void* st) : slot(-1), stream(st) {
+  if (!g_prof_on) return;
+  ProfRec r;
+  r.name = name;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, (cudaStream_t)st);
+  g_prof.push_back(r);
+  slot = (int)g_prof.size() - 1;
+}
+FsProfScope::~FsProfScope() {
+  if (slot >= 0) cudaEventRecord(g_prof[slot].b, (cudaStream_t)stream);
+}
+
+extern "C" int fsnerf_profile_enable(int on) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_prof_on = on != 0;
+  return FSNERF_OK;
+}
+
+extern "C" int fsnerf_profile_read(int max_kernels, char* names, float* total_ms, int* counts) {
+  FS_REQUIRE(names && total_ms && counts && max_kernels > 0, "profile_read: null pointer");
+  int n = 0;
+  for (auto& r : g_prof) {
+    if (cudaEventSynchronize(r.b) != cudaSuccess) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+    int k = 0;
+    for (; k < n; ++k) if (strncmp(names + 32 * k, r.name, 31) == 0) break;
+    if (k == n) {
+      if (n == max_kernels) continue;
+      strncpy(names + 32 * n, r.name, 31);
+      names[32 * n + 31] = 0;
+      total_ms[n] = 0.f; counts[n] = 0;
+      ++n;
+    }
+    total_ms[k] += ms;
+    counts[k] += 1;
+  }
+  return n;
+}
+
+static void* g_trace = nullptr;
+void* fsnerf_debug_trace_ptr() { return g_trace; }
+extern "C" int fsnerf_debug_set_trace(void* buf) {
+  g_trace = buf;
+  return FSNERF_OK;
+}
+
 extern "C" int fsnerf_version(void) { return 100; }
 extern "C" const char* fsnerf_last_error(void) { return g_err; }
 
@@ -89,6 +147,7 @@ extern "C" int fsnerf_mse_loss_grad(int64_t n, const float* rgb, const float* gt
   FS_REQUIRE(rgb && gt, "mse_loss_grad: null pointer");
   if (n <= 0) return FSNERF_OK;
   int threads = 256;
+  FsProfScope prof_("mse_loss_grad", stream);
   mse_loss_grad_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
       n, rgb, gt, grad_scale, loss_sum, d_rgb);
   return fsnerf_check_launch("mse_loss_grad");
@@ -104,6 +163,7 @@ extern "C" int fsnerf_adam_step(int64_t n, float* params, const float* grads, fl
   float step_size = (float)((double)lr / bc1);
   float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
   int threads = 256;
+  FsProfScope prof_("adam", stream);
   adam_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
       n, params, grads, m, v, step_size, beta1, beta2, eps, inv_sqrt_bc2);
   return fsnerf_check_launch("adam_step");

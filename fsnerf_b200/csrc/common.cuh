@@ -12,6 +12,7 @@
 #define FSNERF_ERR_UNSUPPORTED -3
 
 void fsnerf_set_error(const char* fmt, ...);
+void* fsnerf_debug_trace_ptr();
 int fsnerf_check_launch(const char* what);
 
 #define FS_REQUIRE(cond, ...)                 \
@@ -21,6 +22,15 @@ int fsnerf_check_launch(const char* what);
       return FSNERF_ERR_ARG;                  \
     }                                         \
   } while (0)
+
+// Optional per-kernel device timing (cudaEvents on the launch stream), enabled by
+// fsnerf_profile_enable(); bench.py uses it for the live roofline numbers.
+struct FsProfScope {
+  FsProfScope(const char* name, void* stream);
+  ~FsProfScope();
+  int slot;
+  void* stream;
+};
 
 namespace fs {
 
@@ -187,6 +197,22 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
+}
+// relu fused into the fp32 -> bf16x2 conversion
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// packed fp32 add (sm_100: one FADD2 for two lanes)
+__device__ __forceinline__ void add_f32x2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }

@@ -266,6 +266,7 @@ extern "C" int fsnerf_composite_forward(int64_t n_rays, int n_samples, const flo
   composite_fwd_kernel<NB><<<blocks, kWarpsPerBlock * 32, 0, st>>>(                             \
       n_rays, n_samples, raw4, t_starts, t_ends, delta_scale, bkgd, flags, rgb, opacity, depth, \
       weights, alphas, trans)
+  FsProfScope prof_("composite_fwd", stream);
   if (n_samples <= 64) LAUNCH(2);
   else if (n_samples <= 128) LAUNCH(4);
   else if (n_samples <= 192) LAUNCH(6);
@@ -294,6 +295,7 @@ extern "C" int fsnerf_composite_backward(int64_t n_rays, int n_samples, const fl
   composite_bwd_kernel<NB><<<blocks, kWarpsPerBlock * 32, 0, st>>>(                              \
       n_rays, n_samples, raw4, t_starts, t_ends, delta_scale, bkgd, flags, d_rgb, d_opacity,     \
       d_depth, d_weights, d_raw4, d_bkgd)
+  FsProfScope prof_("composite_bwd", stream);
   if (n_samples <= 64) LAUNCH(2);
   else if (n_samples <= 128) LAUNCH(4);
   else if (n_samples <= 192) LAUNCH(6);

@@ -52,6 +52,9 @@ struct BwdArgs {
   uint8_t* dstash;
 };
 
+// sigma / rgb head weights (uniform epilogue operands), see mlp_common.cuh kSmall*
+__constant__ float c_small[kSmallFloats];
+
 __device__ __forceinline__ uint4 ldg_u4(const void* p) {
   return __ldg(reinterpret_cast<const uint4*>(p));
 }
@@ -163,7 +166,6 @@ mlp_dgrad_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant_
     const int row = quarter * 32 + lane;
     const int et = threadIdx.x - 64;
     const uint32_t tmem_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const float* __restrict__ params = args.params;
     const int g_branch = prog.n_gemm - 1;
     uint32_t acc_phase = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -186,32 +188,27 @@ mlp_dgrad_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant_
       {
         const GemmLayer& LB = prog.layer[g_branch];
         const uint8_t* hb = stash_tile + LB.stash_off;
-        const float* __restrict__ wr = params + prog.rgb_w_off;
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          const uint8_t* mrow = hb + (c0 >> 6) * kChunkBytes;
-          const int u0 = (c0 & 63) >> 3;
-          uint32_t packed_w[16];
+        uint4 m[16];  // ReLU mask source: the branch layer's forward output row (128 bf16)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 m4 = ldg_u4(mrow + sw128_off(row, u0 + j));
-            const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+        for (int j = 0; j < 16; ++j)
+          m[j] = ldg_u4(hb + (j >> 3) * kChunkBytes + sw128_off(row, j & 7));
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int col = c0 + 8 * j + 2 * q;
-              float v0 = dz[0] * __ldg(wr + col) + dz[1] * __ldg(wr + 128 + col) +
-                         dz[2] * __ldg(wr + 256 + col);
-              float v1 = dz[0] * __ldg(wr + col + 1) + dz[1] * __ldg(wr + 128 + col + 1) +
-                         dz[2] * __ldg(wr + 256 + col + 1);
-              if ((mw[q] & 0x00007FFFu) == 0u) v0 = 0.f;  // relu'(h) : h == 0 <=> masked
-              if ((mw[q] & 0x7FFF0000u) == 0u) v1 = 0.f;
-              packed_w[4 * j + q] = pack_bf16x2(v0, v1);
-            }
+        for (int j = 0; j < 16; ++j) {
+          const uint32_t mw[4] = {m[j].x, m[j].y, m[j].z, m[j].w};
+          uint32_t pw[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int col = 8 * j + 2 * q;
+            float v0 = dz[0] * c_small[kSmallRgbW + col] + dz[1] * c_small[kSmallRgbW + 128 + col] +
+                       dz[2] * c_small[kSmallRgbW + 256 + col];
+            float v1 = dz[0] * c_small[kSmallRgbW + col + 1] + dz[1] * c_small[kSmallRgbW + 128 + col + 1] +
+                       dz[2] * c_small[kSmallRgbW + 256 + col + 1];
+            if ((mw[q] & 0x00007FFFu) == 0u) v0 = 0.f;  // relu'(h): h == 0 <=> masked
+            if ((mw[q] & 0x7FFF0000u) == 0u) v1 = 0.f;
+            pw[q] = pack_bf16x2(v0, v1);
           }
-          const uint32_t chunk = sbase + kSmemAct + (c0 >> 6) * kChunkBytes;
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            st_shared_v4(chunk + sw128_off(row, u0 + j), packed_w[4 * j], packed_w[4 * j + 1],
-                         packed_w[4 * j + 2], packed_w[4 * j + 3]);
+          st_shared_v4(sbase + kSmemAct + (j >> 3) * kChunkBytes + sw128_off(row, j & 7), pw[0], pw[1],
+                       pw[2], pw[3]);
         }
         fence_proxy_async_smem();
         mbar_arrive(bar_a_ready);
@@ -226,44 +223,54 @@ mlp_dgrad_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant_
       for (int s = 0; s < plan.n_steps; ++s) {
         const BwdStep& S = plan.step[s];
         const GemmLayer& LT = prog.layer[S.target];
+        const uint8_t* mimg = (S.mask_off >= 0) ? stash_tile + S.mask_off : nullptr;
+        const bool add_sigma = S.add_sigma != 0;
+        // masks do not depend on the MMA: fetch chunk 0's before waiting on the accumulator
+        uint4 m[2][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          m[0][j] = mimg ? ldg_u4(mimg + sw128_off(row, j)) : make_uint4(~0u, ~0u, ~0u, ~0u);
         mbar_wait(bar_acc_full, acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
         if (et == 0) bulk_wait_read0();
         named_bar_sync(1, 128);  // act free: MMA, image store and column sums are done
-        const uint8_t* mimg = (S.mask_off >= 0) ? stash_tile + S.mask_off : nullptr;
-        const float* __restrict__ wsg = params + prog.sigma_w_off;
-        for (int c0 = 0; c0 < 256; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem_row + c0, v);
+        uint32_t v[2][32];
+        tmem_ld32(tmem_row, v[0]);
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) {
+          const int c0 = ci * 32;
           tmem_ld_wait();
+          if (ci < 7) {
+            tmem_ld32(tmem_row + c0 + 32, v[(ci + 1) & 1]);
+            const int c1 = c0 + 32;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              m[(ci + 1) & 1][j] = mimg ? ldg_u4(mimg + (c1 >> 6) * kChunkBytes + sw128_off(row, ((c1 & 63) >> 3) + j))
+                                        : make_uint4(~0u, ~0u, ~0u, ~0u);
+          }
+          const uint32_t(&vc)[32] = v[ci & 1];
           const int u0 = (c0 & 63) >> 3;
-          uint32_t packed_w[16];
+          const uint32_t chunk = sbase + kSmemAct + (c0 >> 6) * kChunkBytes;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            uint32_t mw[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-            if (mimg) {
-              const uint4 m4 = ldg_u4(mimg + (c0 >> 6) * kChunkBytes + sw128_off(row, u0 + j));
-              mw[0] = m4.x; mw[1] = m4.y; mw[2] = m4.z; mw[3] = m4.w;
-            }
+            const uint4 m4 = m[ci & 1][j];
+            const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+            uint32_t pw[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int i = 8 * j + 2 * q;
-              float v0 = __uint_as_float(v[i]), v1 = __uint_as_float(v[i + 1]);
-              if (S.add_sigma) {
-                v0 += dsig * __ldg(wsg + c0 + i);
-                v1 += dsig * __ldg(wsg + c0 + i + 1);
+              float v0 = __uint_as_float(vc[i]), v1 = __uint_as_float(vc[i + 1]);
+              if (add_sigma) {
+                v0 = fmaf(dsig, c_small[kSmallSigmaW + c0 + i], v0);
+                v1 = fmaf(dsig, c_small[kSmallSigmaW + c0 + i + 1], v1);
               }
               if ((mw[q] & 0x00007FFFu) == 0u) v0 = 0.f;
               if ((mw[q] & 0x7FFF0000u) == 0u) v1 = 0.f;
-              packed_w[4 * j + q] = pack_bf16x2(v0, v1);
+              pw[q] = pack_bf16x2(v0, v1);
             }
+            st_shared_v4(chunk + sw128_off(row, u0 + j), pw[0], pw[1], pw[2], pw[3]);
           }
-          const uint32_t chunk = sbase + kSmemAct + (c0 >> 6) * kChunkBytes;
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            st_shared_v4(chunk + sw128_off(row, u0 + j), packed_w[4 * j], packed_w[4 * j + 1],
-                         packed_w[4 * j + 2], packed_w[4 * j + 3]);
         }
         tc_fence_before();
         fence_proxy_async_smem();
@@ -440,13 +447,18 @@ struct HeadsArgs {
   float* g_sigma_w; float* g_sigma_b; float* g_rgb_w; float* g_rgb_b;
 };
 
+// 256 threads: thread t owns 16-byte unit (t & 31) [= 8 features of chunk (t&31)>>3]
+// of the 256-wide h image and, if (t & 31) < 16, of the 128-wide hb image; the 8
+// row-groups (t >> 5) split the 128 rows.  Every load is a coalesced 16 B / lane.
 __global__ void __launch_bounds__(256)
 mlp_heads_wgrad_kernel(const __grid_constant__ HeadsArgs a) {
   __shared__ float4 dsm[kTileM];  // (dz0, dz1, dz2, dsigma) per row
-  const int t = threadIdx.x;
-  float acc_s = 0.f, acc_r[3] = {0.f, 0.f, 0.f}, acc_b = 0.f;
-  // element t of a row inside an SW128 image: chunk t/64, 16B unit (t%64)/8, bf16 t%8
-  const int chunk = t >> 6, unit = (t & 63) >> 3, el = t & 7;
+  __shared__ float red[8][32][33];
+  const int t = threadIdx.x, u = t & 31, rg = t >> 5;
+  const int chunk = u >> 3, unit = u & 7;
+  float acc_s[8], acc_r[3][8], acc_b = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { acc_s[e] = 0.f; acc_r[0][e] = acc_r[1][e] = acc_r[2][e] = 0.f; }
   for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     __syncthreads();
     if (t < kTileM) {
@@ -462,16 +474,30 @@ mlp_heads_wgrad_kernel(const __grid_constant__ HeadsArgs a) {
     }
     __syncthreads();
     const uint8_t* rec = a.stash + (size_t)tile * a.stash_tile_bytes;
-    const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(rec + a.h_off + chunk * kChunkBytes);
-    const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(rec + a.hb_off + chunk * kChunkBytes);
+    const uint8_t* h = rec + a.h_off + chunk * kChunkBytes;
+    const uint8_t* hb = rec + a.hb_off + chunk * kChunkBytes;
 #pragma unroll 4
-    for (int r = 0; r < kTileM; ++r) {
+    for (int rr = 0; rr < kTileM / 8; ++rr) {
+      const int r = rg * (kTileM / 8) + rr;
       const float4 d = dsm[r];
-      const int off = (r * 128 + ((unit ^ (r & 7)) << 4)) / 2 + el;
-      acc_s += d.w * __bfloat162float(h[off]);
-      if (t < 128) {
-        const float x = __bfloat162float(hb[off]);
-        acc_r[0] += d.x * x; acc_r[1] += d.y * x; acc_r[2] += d.z * x;
+      const uint32_t off = sw128_off(r, unit);
+      const uint4 hv = ldg_u4(h + off);
+      const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        acc_s[2 * q] = fmaf(d.w, bf16_lo(hw[q]), acc_s[2 * q]);
+        acc_s[2 * q + 1] = fmaf(d.w, bf16_hi(hw[q]), acc_s[2 * q + 1]);
+      }
+      if (u < 16) {
+        const uint4 bv = ldg_u4(hb + off);
+        const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float x0 = bf16_lo(bw[q]), x1 = bf16_hi(bw[q]);
+          acc_r[0][2 * q] = fmaf(d.x, x0, acc_r[0][2 * q]); acc_r[0][2 * q + 1] = fmaf(d.x, x1, acc_r[0][2 * q + 1]);
+          acc_r[1][2 * q] = fmaf(d.y, x0, acc_r[1][2 * q]); acc_r[1][2 * q + 1] = fmaf(d.y, x1, acc_r[1][2 * q + 1]);
+          acc_r[2][2 * q] = fmaf(d.z, x0, acc_r[2][2 * q]); acc_r[2][2 * q + 1] = fmaf(d.z, x1, acc_r[2][2 * q + 1]);
+        }
       }
     }
     if (t >= 128 && t < 132) {  // bias sums: 4 threads, one component each
@@ -482,11 +508,28 @@ mlp_heads_wgrad_kernel(const __grid_constant__ HeadsArgs a) {
       }
     }
   }
-  atomicAdd(a.g_sigma_w + t, acc_s);
-  if (t < 128) {
-    atomicAdd(a.g_rgb_w + t, acc_r[0]);
-    atomicAdd(a.g_rgb_w + 128 + t, acc_r[1]);
-    atomicAdd(a.g_rgb_w + 256 + t, acc_r[2]);
+  // combine the 8 row-groups through shared memory, then one atomic per feature
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[rg][u][e] = acc_s[e];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[rg][u][8 + 8 * c + e] = acc_r[c][e];
+  __syncthreads();
+  {
+    // thread t -> feature t of h (sigma head): unit t>>3, element t&7
+    float s = 0.f;
+    for (int g = 0; g < 8; ++g) s += red[g][t >> 3][t & 7];
+    atomicAdd(a.g_sigma_w + t, s);
+    if (t < 128) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float r3 = 0.f;
+        for (int g = 0; g < 8; ++g) r3 += red[g][t >> 3][8 + 8 * c + (t & 7)];
+        atomicAdd(a.g_rgb_w + c * 128 + t, r3);
+      }
+    }
   }
   if (t >= 128 && t < 131) atomicAdd(a.g_rgb_b + (t - 128), acc_b);
   if (t == 131) atomicAdd(a.g_sigma_b, acc_b);
@@ -555,7 +598,18 @@ extern "C" int fsnerf_mlp_backward(const fsnerf_net_cfg* cfg, const float* param
   ba.stash = reinterpret_cast<const uint8_t*>(stash); ba.out = out; ba.d_out = d_out;
   ba.grads = grads; ba.dstash = reinterpret_cast<uint8_t*>(workspace);
   int grid = (int)(n_tiles < 2 * kNumSMs ? n_tiles : 2 * kNumSMs);
-  mlp_dgrad_kernel<<<grid, kThreads, kSmemTotal, st>>>(P, BP, ba);
+  {
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_small, ba.packed + P.small_off, kSmallFloats * sizeof(float), 0,
+                                            cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) {
+      fsnerf_set_error("mlp_backward: constant upload: %s", cudaGetErrorString(e));
+      return FSNERF_ERR_CUDA;
+    }
+  }
+  {
+    FsProfScope prof_("mlp_dgrad", stream);
+    mlp_dgrad_kernel<<<grid, kThreads, kSmemTotal, st>>>(P, BP, ba);
+  }
   rc = fsnerf_check_launch("mlp_backward(dgrad)");
   if (rc != FSNERF_OK) return rc;
   // ---- heads
@@ -566,7 +620,10 @@ extern "C" int fsnerf_mlp_backward(const fsnerf_net_cfg* cfg, const float* param
   ha.g_sigma_w = grads + P.sigma_w_off; ha.g_sigma_b = grads + P.sigma_b_off;
   ha.g_rgb_w = grads + P.rgb_w_off; ha.g_rgb_b = grads + P.rgb_b_off;
   int hgrid = (int)(n_tiles < 4 * kNumSMs ? n_tiles : 4 * kNumSMs);
-  mlp_heads_wgrad_kernel<<<hgrid, 256, 0, st>>>(ha);
+  {
+    FsProfScope prof_("mlp_heads_wgrad", stream);
+    mlp_heads_wgrad_kernel<<<hgrid, 256, 0, st>>>(ha);
+  }
   rc = fsnerf_check_launch("mlp_backward(heads)");
   if (rc != FSNERF_OK) return rc;
   // ---- wgrad plan: (layer, input part) jobs, CTAs split proportionally to the bytes they stream
@@ -607,6 +664,7 @@ extern "C" int fsnerf_mlp_backward(const fsnerf_net_cfg* cfg, const float* param
   WgradArgs wa;
   wa.stash = ba.stash; wa.dstash = ba.dstash; wa.stash_tile_bytes = P.stash_tile_bytes;
   wa.dstash_tile_bytes = P.dstash_tile_bytes; wa.n_tiles = n_tiles; wa.grads = grads;
+  FsProfScope prof_("mlp_wgrad", stream);
   mlp_wgrad_kernel<<<WP.n_ctas, kThreads, kWSmemTotal, st>>>(WP, wa);
   return fsnerf_check_launch("mlp_backward(wgrad)");
 }

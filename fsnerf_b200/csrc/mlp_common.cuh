@@ -22,6 +22,15 @@ constexpr int kBlockBytes = 16384;   // one [128 x 64] bf16 SW128 block
 constexpr int kChunkBytes = 16384;   // one K-chunk of an activation tile (128 rows x 128 B)
 constexpr int kMaxGemm = 16;
 constexpr int kMaxFreqs = 10;        // 3*(1+2L) <= 64
+// "small params" block appended to the packed image: fp32 copies of every bias and
+// of the sigma / rgb head weights, contiguous so ONE device-to-device copy moves
+// them into __constant__ memory (uniform operands of the epilogue FADD/FFMA).
+constexpr int kSmallBias = 0;                       // [kMaxGemm][256]
+constexpr int kSmallSigmaW = kMaxGemm * 256;        // [256]
+constexpr int kSmallRgbW = kSmallSigmaW + 256;      // [3][128]
+constexpr int kSmallSigmaB = kSmallRgbW + 384;      // [1]
+constexpr int kSmallRgbB = kSmallSigmaB + 1;        // [3]
+constexpr int kSmallFloats = 4864;                  // padded
 
 enum Epi : int {
   EPI_RELU = 0,        // h = relu(acc + b) -> act
@@ -54,6 +63,7 @@ struct MlpProgram {
   int n_blocks_bwd;
   int d_pos, d_dir;    // encoding widths (63, 27)
   int n_freqs_pos, n_freqs_dir;
+  int pow2_freqs;      // 1: f_k = 2^k exactly (log_space) -> double-angle recurrence in the encoder
   float freq_pos[kMaxFreqs], freq_dir[kMaxFreqs];
   int sigma_w_off, sigma_b_off, rgb_w_off, rgb_b_off;
   int stash_aux_pos_off, stash_aux_dir_off;  // byte offsets in the tile record
@@ -63,7 +73,8 @@ struct MlpProgram {
   int n_tensors;         // state-dict tensors (2 per Linear)
   int64_t tensor_off[2 * kMaxGemm + 8];
   int64_t tensor_numel[2 * kMaxGemm + 8];
-  int64_t packed_bytes;
+  int64_t packed_bytes;  // operand blocks + the small-params block
+  int64_t small_off;     // byte offset of the small-params block in the packed image
   GemmLayer layer[kMaxGemm];
 };
 

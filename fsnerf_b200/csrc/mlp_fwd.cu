@@ -13,22 +13,34 @@
 //               ReLU -> bf16 -> the next layer's A tile in smem (activations
 //               never leave the SM); sigma / rgb heads on CUDA cores.
 // Optional stash: each A tile image is bulk-stored to HBM for the backward.
+#include <stdlib.h>
 #include "common.cuh"
 #include "mlp_common.cuh"
 
 namespace fs {
 namespace {
 
-constexpr int kStages = 2;
 constexpr int kFwdThreads = 192;
 constexpr int kSmemAct = 0;                                   // 4 chunks x 16 KB
 constexpr int kSmemAux = kSmemAct + 4 * kChunkBytes;          // 16 KB
 constexpr int kSmemRing = kSmemAux + kChunkBytes;             // kStages x 16 KB
-constexpr int kSmemBars = kSmemRing + kStages * kBlockBytes;  // barriers
-constexpr int kSmemTotal = kSmemBars + 128;
+template <int kStages> __host__ __device__ constexpr int smem_bars() { return kSmemRing + kStages * kBlockBytes; }
+template <int kStages> __host__ __device__ constexpr int smem_total() { return smem_bars<kStages>() + 256; }
 constexpr int kTmemCols = 256;
 
+// fp32 biases + sigma/rgb head weights of the network being evaluated (copied
+// device-to-device from the packed image's small-params block before each launch)
+__constant__ float c_small[kSmallFloats];
+
+// optional per-phase clock64 trace of CTA 0 (fsnerf_debug_set_trace), tuning aid
+#define FS_TRACE(slot, g_, k_)                                                              \
+  do {                                                                                      \
+    if (args.trace && blockIdx.x == 0 && (slot) < 4)                                        \
+      args.trace[((slot) * 16 + (g_)) * 8 + (k_)] = clock64();                              \
+  } while (0)
+
 struct FwdArgs {
+  long long* trace;
   const float* params;
   const uint8_t* packed;
   int64_t n_samples;
@@ -49,22 +61,46 @@ struct FwdArgs {
 // sin/cos encoding of v[3] -> 64 bf16 channels (zero padded) into row `row` of a
 // [128 x 64] SW128 tile at smem address `tile`.
 // reference: src/core/models.py:43-50 (channel order x, sin(f0 x), cos(f0 x), ...)
-__device__ __forceinline__ void encode_row(const float v[3], int n_freqs, const float* freqs,
+__device__ __forceinline__ void encode_row(const float v[3], int n_freqs, const float* freqs, bool pow2,
                                            const float* __restrict__ mask, uint32_t tile, int row) {
   float ch[64];
 #pragma unroll
   for (int i = 0; i < 64; ++i) ch[i] = 0.f;
   ch[0] = v[0]; ch[1] = v[1]; ch[2] = v[2];
+  if (pow2) {
+    // f_k = 2^k (log_space, the reference default): an accurate sincosf every 4th octave,
+    // exact double-angle steps (sin 2a = 2 s c, cos 2a = 1 - 2 s^2) in between.  The error
+    // doubles per step, so it stays <= ~8 ulp (1e-6) — invisible after the bf16 rounding.
 #pragma unroll
-  for (int k = 0; k < kMaxFreqs; ++k) {
-    if (k < n_freqs) {
-      float f = freqs[k];
+    for (int a = 0; a < 3; ++a) {
+      float sn = 0.f, cs = 1.f;
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        float s, c;
-        sincosf(v[a] * f, &s, &c);
-        ch[3 + 6 * k + a] = s;
-        ch[3 + 6 * k + 3 + a] = c;
+      for (int k = 0; k < kMaxFreqs; ++k) {
+        if (k < n_freqs) {
+          if ((k & 3) == 0) {
+            sincosf(v[a] * freqs[k], &sn, &cs);
+          } else {
+            const float s2 = 2.0f * sn * cs;
+            cs = fmaf(-2.0f * sn, sn, 1.0f);
+            sn = s2;
+          }
+          ch[3 + 6 * k + a] = sn;
+          ch[3 + 6 * k + 3 + a] = cs;
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kMaxFreqs; ++k) {
+      if (k < n_freqs) {
+        float f = freqs[k];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          float sn, cs;
+          sincosf(v[a] * f, &sn, &cs);
+          ch[3 + 6 * k + a] = sn;
+          ch[3 + 6 * k + 3 + a] = cs;
+        }
       }
     }
   }
@@ -82,11 +118,13 @@ __device__ __forceinline__ void encode_row(const float v[3], int n_freqs, const 
   }
 }
 
-__global__ void __launch_bounds__(kFwdThreads, 2)
+template <int kStages, int kMinBlocks>
+__global__ void __launch_bounds__(kFwdThreads, kMinBlocks)
 mlp_fwd_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ FwdArgs args) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kSmemBars = smem_bars<kStages>();
   const uint32_t bar_w_full = sbase + kSmemBars;            // [kStages]
   const uint32_t bar_w_empty = bar_w_full + 8 * kStages;    // [kStages]
   const uint32_t bar_a_ready = bar_w_empty + 8 * kStages;
@@ -95,6 +133,9 @@ mlp_fwd_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ 
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + kSmemBars + 8 * (2 * kStages + 2));
 
   const int n_gemm = args.density_only ? prog.n_hidden : prog.n_gemm;
+  int dir_after = 0;  // last hidden layer whose MMA reads the aux (position encoding) buffer
+  for (int g = 0; g < prog.n_hidden; ++g)
+    if (prog.layer[g].use_aux) dir_after = g;
   const int n_blocks = args.density_only ? prog.n_blocks_fwd_density : prog.n_blocks_fwd;
   const int64_t n_tiles = (args.n_samples + kTileM - 1) / kTileM;
 
@@ -139,12 +180,15 @@ mlp_fwd_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ 
     // ------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
     uint32_t cnt = 0, a_phase = 0;
+    int titer = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int g = 0; g < n_gemm; ++g) {
         const GemmLayer& L = prog.layer[g];
+        if (lane == 0) FS_TRACE(titer, g, 0);
         mbar_wait(bar_a_ready, a_phase);
         a_phase ^= 1;
         tc_fence_after();
+        if (lane == 0) FS_TRACE(titer, g, 1);
         const int nchunks = L.n_act_chunks + L.use_aux;
         for (int c = 0; c < nchunks; ++c) {
           const uint32_t a_tile =
@@ -167,8 +211,10 @@ mlp_fwd_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ 
           }
         }
         if (lane == 0) umma_commit(bar_acc_full);
+        if (lane == 0) FS_TRACE(titer, g, 2);
         __syncwarp();
       }
+      ++titer;
     }
   } else {
     // ------------------------------------------------ encode + epilogue (thread = sample row)
@@ -176,9 +222,11 @@ mlp_fwd_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ 
     const int row = quarter * 32 + lane;
     const int et = threadIdx.x - 64;  // 0..127
     const uint32_t tmem_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const float* __restrict__ params = args.params;
     uint32_t acc_phase = 0;
+    int titer = -1;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      ++titer;
+      if (et == 0) FS_TRACE(titer, 15, 6);
       const int64_t p = tile * kTileM + row;
       const bool valid = p < args.n_samples;
       uint8_t* stash_tile = args.stash ? args.stash + (size_t)tile * prog.stash_tile_bytes : nullptr;
@@ -202,12 +250,14 @@ mlp_fwd_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ 
           }
         }
       }
-      // previous tile's stash stores must have finished reading aux/act
-      if (et == 0) bulk_wait_read0();
-      named_bar_sync(1, 128);
-      encode_row(pos, prog.n_freqs_pos, prog.freq_pos, args.mask_pos, sbase + kSmemAux, row);
+      if (stash_tile) {  // previous tile's image stores must have finished reading aux/act
+        if (et == 0) bulk_wait_read0();
+        named_bar_sync(1, 128);
+      }
+      encode_row(pos, prog.n_freqs_pos, prog.freq_pos, prog.pow2_freqs != 0, args.mask_pos, sbase + kSmemAux, row);
       fence_proxy_async_smem();
       mbar_arrive(bar_a_ready);
+      if (et == 0) FS_TRACE(titer, 15, 7);
       if (stash_tile) {
         named_bar_sync(1, 128);
         if (et == 0) {
@@ -218,78 +268,90 @@ mlp_fwd_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ 
       float sigma = 0.f;
       for (int g = 0; g < n_gemm; ++g) {
         const GemmLayer& L = prog.layer[g];
+        if (et == 0) FS_TRACE(titer, g, 3);
         mbar_wait(bar_acc_full, acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
-        if (et == 0) bulk_wait_read0();
-        named_bar_sync(1, 128);
-        const float* __restrict__ bias = params + L.bias_off;
+        if (et == 0) FS_TRACE(titer, g, 4);
+        if (stash_tile) {  // the previous image store must have finished reading act
+          if (et == 0) bulk_wait_read0();
+          named_bar_sync(1, 128);
+        }
         const int ncols = L.n_halves * 128;
+        const int epi = L.epi;
         float rgb_acc[3] = {0.f, 0.f, 0.f};
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem_row + c0, v);
-          tmem_ld_wait();
-          float h[32];
+        // software pipeline: the TMEM load of chunk ci+1 is in flight while chunk ci is
+        // converted; bias / head weights are uniform __constant__ operands (no loads)
+        uint32_t v[2][32];
+        tmem_ld32(tmem_row, v[0]);
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
-            h[i] = __uint_as_float(v[i]) + b4.x;
-            h[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
-            h[i + 2] = __uint_as_float(v[i + 2]) + b4.z;
-            h[i + 3] = __uint_as_float(v[i + 3]) + b4.w;
-          }
-          if (L.epi != EPI_CONN) {
+        for (int ci = 0; ci < 8; ++ci) {
+          const int c0 = ci * 32;
+          if (c0 < ncols) {
+            tmem_ld_wait();
+            if (c0 + 32 < ncols) tmem_ld32(tmem_row + c0 + 32, v[(ci + 1) & 1]);
+            const uint32_t(&vc)[32] = v[ci & 1];
+            const float2* __restrict__ cb2 =
+                reinterpret_cast<const float2*>(c_small + kSmallBias + g * 256 + c0);
+            uint32_t w[16];
+            if (epi == EPI_RELU || epi == EPI_CONN) {
+              // hot path: packed fp32 bias add (FADD2) + relu fused into the bf16x2 convert
 #pragma unroll
-            for (int i = 0; i < 32; ++i) h[i] = fmaxf(h[i], 0.f);
-          }
-          if (L.epi == EPI_RELU_SIGMA) {
-            const float* __restrict__ ws = params + prog.sigma_w_off + c0;
+              for (int i = 0; i < 16; ++i) {
+                const float2 b = cb2[i];
+                float s0, s1;
+                add_f32x2(s0, s1, __uint_as_float(vc[2 * i]), __uint_as_float(vc[2 * i + 1]), b.x, b.y);
+                w[i] = (epi == EPI_RELU) ? pack_bf16x2_relu(s0, s1) : pack_bf16x2(s0, s1);
+              }
+            } else {
+              float h[32];
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 w4 = __ldg(reinterpret_cast<const float4*>(ws + i));
-              sigma += h[i] * w4.x + h[i + 1] * w4.y + h[i + 2] * w4.z + h[i + 3] * w4.w;
-            }
-          } else if (L.epi == EPI_BRANCH) {
+              for (int i = 0; i < 16; ++i) {
+                const float2 b = cb2[i];
+                h[2 * i] = fmaxf(__uint_as_float(vc[2 * i]) + b.x, 0.f);
+                h[2 * i + 1] = fmaxf(__uint_as_float(vc[2 * i + 1]) + b.y, 0.f);
+                w[i] = pack_bf16x2(h[2 * i], h[2 * i + 1]);
+              }
+              if (epi == EPI_RELU_SIGMA) {
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-              const float* __restrict__ wr = params + prog.rgb_w_off + ch * 128 + c0;
+                for (int i = 0; i < 32; ++i) sigma = fmaf(h[i], c_small[kSmallSigmaW + c0 + i], sigma);
+              } else {
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + i));
-                rgb_acc[ch] += h[i] * w4.x + h[i + 1] * w4.y + h[i + 2] * w4.z + h[i + 3] * w4.w;
+                for (int ch = 0; ch < 3; ++ch) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i)
+                    rgb_acc[ch] = fmaf(h[i], c_small[kSmallRgbW + ch * 128 + c0 + i], rgb_acc[ch]);
+                }
               }
             }
-          }
-          // bf16 -> the next A tile (chunk = 64 columns = 128 B per row)
-          const uint32_t chunk = sbase + kSmemAct + (c0 >> 6) * kChunkBytes;
-          const int u0 = (c0 & 63) >> 3;
+            // bf16 -> the next A tile (chunk = 64 columns = 128 B per row)
+            const uint32_t chunk = sbase + kSmemAct + (c0 >> 6) * kChunkBytes;
+            const int u0 = (c0 & 63) >> 3;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            st_shared_v4(chunk + sw128_off(row, u0 + j), pack_bf16x2(h[8 * j], h[8 * j + 1]),
-                         pack_bf16x2(h[8 * j + 2], h[8 * j + 3]),
-                         pack_bf16x2(h[8 * j + 4], h[8 * j + 5]),
-                         pack_bf16x2(h[8 * j + 6], h[8 * j + 7]));
+            for (int j = 0; j < 4; ++j)
+              st_shared_v4(chunk + sw128_off(row, u0 + j), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
           }
         }
-        if (L.epi == EPI_RELU_SIGMA) sigma += __ldg(params + prog.sigma_b_off);
-        if (L.epi == EPI_CONN) {
-          // view-direction encoding for the branch layer (aux is free: its last
-          // reader was the skip layer's MMA, long complete)
-          encode_row(dir, prog.n_freqs_dir, prog.freq_dir, args.mask_dir, sbase + kSmemAux, row);
-        }
+        if (epi == EPI_RELU_SIGMA) sigma += c_small[kSmallSigmaB];
         tc_fence_before();
         fence_proxy_async_smem();
         const bool last = (g == n_gemm - 1);
         if (!last) mbar_arrive(bar_a_ready);
+        if (et == 0) FS_TRACE(titer, g, 5);
         if (stash_tile) {
           named_bar_sync(1, 128);
           if (et == 0) {
             bulk_s2g(stash_tile + L.stash_off, sbase + kSmemAct, (ncols >> 6) * kChunkBytes);
-            if (L.epi == EPI_CONN)
+            if (epi == EPI_CONN)
               bulk_s2g(stash_tile + prog.stash_aux_dir_off, sbase + kSmemAux, kChunkBytes);
             bulk_commit();
           }
+        }
+        if (g == dir_after && !args.density_only) {
+          // view-direction encoding for the branch layer, overlapped with the next layer's
+          // MMAs: aux is free (its last reader, this layer's MMA, has completed) and the
+          // fence.proxy.async of the following epilogues publishes it before the branch MMA
+          encode_row(dir, prog.n_freqs_dir, prog.freq_dir, prog.pow2_freqs != 0, args.mask_dir, sbase + kSmemAux, row);
         }
         if (last && valid) {
           if (args.density_only) {
@@ -298,7 +360,7 @@ mlp_fwd_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ 
             float r3[3];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-              float z = rgb_acc[ch] + __ldg(params + prog.rgb_b_off + ch);
+              float z = rgb_acc[ch] + c_small[kSmallRgbB + ch];
               r3[ch] = 1.0f / (1.0f + expf(-z));
             }
             reinterpret_cast<float4*>(args.out)[p] = make_float4(r3[0], r3[1], r3[2], sigma);
@@ -343,24 +405,42 @@ extern "C" int fsnerf_mlp_forward(const fsnerf_net_cfg* cfg, const float* params
              "mlp_forward: params/out must be 16B aligned, packed/stash 128B aligned");
   FS_REQUIRE(!(stash && density_only), "mlp_forward: stash (training) needs the full network");
   if (n_samples == 0) return FSNERF_OK;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kSmemTotal);
-    if (e != cudaSuccess) {
-      fsnerf_set_error("mlp_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("FSNERF_FWD_VARIANT");
+    variant = e ? atoi(e) : 0;
+    cudaError_t e1 = cudaFuncSetAttribute(mlp_fwd_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          smem_total<2>());
+    cudaError_t e2 = cudaFuncSetAttribute(mlp_fwd_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          smem_total<8>());
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      fsnerf_set_error("mlp_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+      variant = -1;
       return FSNERF_ERR_CUDA;
     }
-    configured = true;
   }
   FwdArgs a;
+  a.trace = reinterpret_cast<long long*>(fsnerf_debug_trace_ptr());
   a.params = params; a.packed = reinterpret_cast<const uint8_t*>(packed);
   a.n_samples = n_samples; a.samples_per_ray = samples_per_ray;
   a.rays_o = rays_o; a.rays_d = rays_d; a.t_starts = t_starts; a.t_ends = t_ends;
   a.x = x; a.dirs = dirs; a.mask_pos = mask_pos; a.mask_dir = mask_dir;
   a.density_only = density_only; a.out = out; a.stash = reinterpret_cast<uint8_t*>(stash);
   int64_t n_tiles = (n_samples + kTileM - 1) / kTileM;
-  int grid = (int)(n_tiles < 2 * kNumSMs ? n_tiles : 2 * kNumSMs);
-  mlp_fwd_kernel<<<grid, kFwdThreads, kSmemTotal, (cudaStream_t)stream>>>(P, a);
+  const int ctas_per_sm = (variant == 1) ? 1 : 2;
+  int grid = (int)(n_tiles < ctas_per_sm * kNumSMs ? n_tiles : ctas_per_sm * kNumSMs);
+  {
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_small, a.packed + P.small_off, kSmallFloats * sizeof(float), 0,
+                                            cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+      fsnerf_set_error("mlp_forward: constant upload: %s", cudaGetErrorString(e));
+      return FSNERF_ERR_CUDA;
+    }
+  }
+  FsProfScope prof_(stash ? "mlp_fwd_train" : "mlp_fwd", stream);
+  if (variant == 1)
+    mlp_fwd_kernel<8, 1><<<grid, kFwdThreads, smem_total<8>(), (cudaStream_t)stream>>>(P, a);
+  else
+    mlp_fwd_kernel<2, 2><<<grid, kFwdThreads, smem_total<2>(), (cudaStream_t)stream>>>(P, a);
   return fsnerf_check_launch("mlp_forward");
 }

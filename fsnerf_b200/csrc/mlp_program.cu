@@ -21,6 +21,7 @@ int build_program(const fsnerf_net_cfg* cfg, MlpProgram* P) {
   P->n_hidden = n;
   P->n_freqs_pos = cfg->n_freqs_pos;
   P->n_freqs_dir = cfg->n_freqs_dir;
+  P->pow2_freqs = cfg->log_space ? 1 : 0;
   P->d_pos = 3 * (1 + 2 * cfg->n_freqs_pos);
   P->d_dir = 3 * (1 + 2 * cfg->n_freqs_dir);
   // frequencies exactly as torch builds them (src/core/models.py:30-34)
@@ -116,7 +117,8 @@ int build_program(const fsnerf_net_cfg* cfg, MlpProgram* P) {
   }
   P->dstash_tile_bytes = dst;
   P->n_blocks_bwd = blk - P->n_blocks_fwd;
-  P->packed_bytes = (int64_t)blk * kBlockBytes;
+  P->small_off = (int64_t)blk * kBlockBytes;
+  P->packed_bytes = P->small_off + (int64_t)kSmallFloats * 4;
   return FSNERF_OK;
 }
 
@@ -129,12 +131,35 @@ struct PackBlk {
 constexpr int kMaxPackBlk = 192;
 struct PackTable {
   int n;
+  int n_gemm;
+  int bias_off[kMaxGemm], bias_n[kMaxGemm];
+  int sigma_w_off, sigma_b_off, rgb_w_off, rgb_b_off;
   PackBlk b[kMaxPackBlk];
 };
 
 __global__ void __launch_bounds__(256)
 pack_kernel(const __grid_constant__ PackTable T, const float* __restrict__ params,
             uint8_t* __restrict__ packed) {
+  if ((int)blockIdx.x == T.n) {  // last CTA: the contiguous fp32 small-params block
+    float* sm = reinterpret_cast<float*>(packed + (size_t)T.n * kBlockBytes);
+    for (int i = threadIdx.x; i < kSmallFloats; i += blockDim.x) {
+      float v = 0.f;
+      if (i < kSmallSigmaW) {
+        int g = i >> 8, c = i & 255;
+        if (g < T.n_gemm && c < T.bias_n[g]) v = params[T.bias_off[g] + c];
+      } else if (i < kSmallRgbW) {
+        v = params[T.sigma_w_off + (i - kSmallSigmaW)];
+      } else if (i < kSmallSigmaB) {
+        v = params[T.rgb_w_off + (i - kSmallRgbW)];
+      } else if (i == kSmallSigmaB) {
+        v = params[T.sigma_b_off];
+      } else if (i < kSmallRgbB + 3) {
+        v = params[T.rgb_b_off + (i - kSmallRgbB)];
+      }
+      sm[i] = v;
+    }
+    return;
+  }
   const PackBlk b = T.b[blockIdx.x];
   uint8_t* dst = packed + (size_t)blockIdx.x * kBlockBytes;
   const float* W = params + b.w_off;
@@ -228,6 +253,14 @@ extern "C" int fsnerf_mlp_pack(const fsnerf_net_cfg* cfg, const float* params, v
   }
   FS_REQUIRE(T.n == P.n_blocks_fwd + P.n_blocks_bwd && T.n <= kMaxPackBlk,
              "mlp_pack: internal block count mismatch");
-  pack_kernel<<<T.n, 256, 0, (cudaStream_t)stream>>>(T, params, reinterpret_cast<uint8_t*>(packed));
+  FsProfScope prof_("mlp_pack", stream);
+  T.n_gemm = P.n_gemm;
+  for (int g = 0; g < P.n_gemm; ++g) {
+    T.bias_off[g] = P.layer[g].bias_off;
+    T.bias_n[g] = P.layer[g].n_halves * 128;
+  }
+  T.sigma_w_off = P.sigma_w_off; T.sigma_b_off = P.sigma_b_off;
+  T.rgb_w_off = P.rgb_w_off; T.rgb_b_off = P.rgb_b_off;
+  pack_kernel<<<T.n + 1, 256, 0, (cudaStream_t)stream>>>(T, params, reinterpret_cast<uint8_t*>(packed));
   return fsnerf_check_launch("mlp_pack");
 }

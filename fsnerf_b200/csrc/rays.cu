@@ -228,6 +228,7 @@ extern "C" int fsnerf_gen_rays(const float* poses, int n_views, int pose_rows, i
   if (n_rays == 0) return FSNERF_OK;
   int threads = 256;
   int64_t blocks = (n_rays + threads - 1) / threads;
+  FsProfScope prof_("gen_rays", stream);
   gen_rays_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
       poses, n_views, pose_rows, H, W, focal, pixel_ids, first_id, n_rays, ndc, ndc_near, ndc_sx,
       ndc_sy, images, rays_o, rays_d, rgb_gt);
@@ -240,6 +241,7 @@ extern "C" int fsnerf_to_ndc(const float* rays_o, const float* rays_d, int64_t n
   FS_REQUIRE(rays_o && rays_d && ndc_o && ndc_d, "to_ndc: null pointer");
   int threads = 256;
   int64_t blocks = (n_rays + threads - 1) / threads;
+  FsProfScope prof_("to_ndc", stream);
   to_ndc_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(rays_o, rays_d, n_rays,
                                                                         near, sx, sy, ndc_o, ndc_d);
   return fsnerf_check_launch("to_ndc");
@@ -253,6 +255,7 @@ extern "C" int fsnerf_sample_stratified(int64_t n_rays, int n_samples, float nea
   FS_REQUIRE(t_starts && t_ends, "sample_stratified: null output");
   int64_t n = n_rays * n_samples;
   int threads = 256;
+  FsProfScope prof_("sample_stratified", stream);
   stratified_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
       n_rays, n_samples, near, far, u, t_starts, t_ends);
   return fsnerf_check_launch("sample_stratified");
@@ -270,6 +273,7 @@ extern "C" int fsnerf_sample_pdf(int64_t n_rays, int n_coarse, int n_fine, const
   size_t smem = (size_t)kPdfWarps * (2 * (n_coarse - 1) + 2 * (n_coarse + n_fine)) * sizeof(float);
   FS_REQUIRE(smem <= 48 * 1024, "sample_pdf: n_coarse+n_fine too large for shared memory");
   int64_t blocks = (n_rays + kPdfWarps - 1) / kPdfWarps;
+  FsProfScope prof_("sample_pdf", stream);
   sample_pdf_kernel<<<(unsigned)blocks, kPdfWarps * 32, smem, (cudaStream_t)stream>>>(
       n_rays, n_coarse, n_fine, z_coarse, w_coarse, u, far, samples, inds, perm, t_starts, t_ends);
   return fsnerf_check_launch("sample_pdf");

@@ -241,3 +241,21 @@ def adam_step(params, grads, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
     check(_lib.load().fsnerf_adam_step(params.numel(), ptr(params), ptr(grads), ptr(m), ptr(v),
                                        float(lr), beta1, beta2, eps, int(step), _stream()),
           "fsnerf_adam_step")
+
+
+# -------------------------------------------------------------- profiling
+def profile_enable(on=True):
+    check(_lib.load().fsnerf_profile_enable(int(bool(on))), "fsnerf_profile_enable")
+
+
+def profile_read():
+    """-> {kernel name: (total_ms, launches)} since profile_enable(True)"""
+    n_max = 32
+    names = C.create_string_buffer(32 * n_max)
+    ms = (C.c_float * n_max)()
+    cnt = (C.c_int * n_max)()
+    n = _lib.load().fsnerf_profile_read(n_max, names, ms, cnt)
+    if n < 0:
+        check(n, "fsnerf_profile_read")
+    raw = names.raw
+    return {raw[32 * i:32 * (i + 1)].split(b"\0")[0].decode(): (ms[i], cnt[i]) for i in range(n)}

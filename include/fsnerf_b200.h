@@ -145,6 +145,17 @@ int fsnerf_mse_loss_grad(int64_t n, const float* rgb, const float* gt, float gra
 int fsnerf_adam_step(int64_t n, float* params, const float* grads, float* m, float* v, float lr,
                      float beta1, float beta2, float eps, int step, void* stream);
 
+/* ---- measurement aid (bench.py): per-kernel device time ------------------ */
+/* on != 0: start recording a cudaEvent pair around every kernel this library
+ * launches (on the launch stream); 0: stop and drop the records. */
+int fsnerf_profile_enable(int on);
+/* Sum the recorded times by kernel name (synchronises the recorded events).
+ * names: max_kernels x 32 chars; returns the number of distinct kernels. */
+int fsnerf_profile_read(int max_kernels, char* names, float* total_ms, int* counts);
+/* tuning aid: device buffer of >= 4*16*8 int64 that CTA 0 of the MLP forward fills
+ * with clock64 phase timestamps (NULL disables; tools/trace_fwd.py decodes it). */
+int fsnerf_debug_set_trace(void* buf);
+
 #ifdef __cplusplus
 }
 #endif

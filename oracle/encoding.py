@@ -30,6 +30,23 @@ def positional_encoding(x, n_freqs, log_space=True):
     return torch.cat(out, -1)
 
 
+def positional_encoding_doubleangle(x, n_freqs):
+    """The CUDA encoder's evaluation order for f_k = 2^k (log_space): an accurate
+    sin/cos every 4th octave, double-angle steps sin 2a = 2 s c, cos 2a = 1 - 2 s^2 in
+    between.  Equal to positional_encoding(x, n_freqs, True) to ~1e-6 absolute; used by
+    the bf16 emulation so that both sides round (almost always) the same values to bf16."""
+    out = [x]
+    sn = cs = None
+    for k in range(n_freqs):
+        if k % 4 == 0:
+            sn, cs = torch.sin(x * (2.0 ** k)), torch.cos(x * (2.0 ** k))
+        else:
+            sn, cs = 2.0 * sn * cs, 1.0 - 2.0 * sn * sn
+        out.append(sn)
+        out.append(cs)
+    return torch.cat(out, -1)
+
+
 def freq_mask(d_out, step, reg_steps, clip=False):
     """FreeNeRF mask over an encoding of d_out channels in groups of 3
     (SURVEY.md Appendix B4).  step >= reg_steps (or reg_steps <= 0) -> ones.

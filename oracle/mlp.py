@@ -9,7 +9,7 @@ it must reproduce reference NeRF.forward bit-for-bit on the same host
 import torch
 import torch.nn.functional as F
 
-from .encoding import positional_encoding
+from .encoding import positional_encoding, positional_encoding_doubleangle
 
 
 def init_state_dict(n_layers=8, d_hidden=256, skip=(4,), n_freqs=10,
@@ -100,7 +100,9 @@ def nerf_forward_bf16emu(sd, x, dirs, n_layers=8, skip=(4,), n_freqs=10, n_freqs
         pre = F.linear(h_r, _r(sd[f"{name}.weight"]), sd[f"{name}.bias"])
         return _RoundGradBf16.apply(pre)
 
-    x_in = positional_encoding(x, n_freqs, log_space)
+    enc = (lambda v, L: positional_encoding_doubleangle(v, L)) if log_space else (
+        lambda v, L: positional_encoding(v, L, log_space))
+    x_in = enc(x, n_freqs)
     if mask_pos is not None:
         x_in = x_in * mask_pos
     x_in = x_in.bfloat16().float()
@@ -115,7 +117,7 @@ def nerf_forward_bf16emu(sd, x, dirs, n_layers=8, skip=(4,), n_freqs=10, n_freqs
             h_r = torch.cat([h_r, x_in], -1)
     sigma = F.linear(h, sd["sigma.weight"], sd["sigma.bias"])  # fp32 head on CUDA cores
     c_r = _r(lin(h_r, "connection"))
-    d_in = positional_encoding(dirs, n_freqs_dir, log_space)
+    d_in = enc(dirs, n_freqs_dir)
     if mask_dir is not None:
         d_in = d_in * mask_dir
     d_in = d_in.bfloat16().float()

@@ -39,8 +39,8 @@ def test_host_side_layout_queries():
     assert len(layout) == 24 and sum(n for _, n in layout) == 595844  # reference state dict
     assert all(o % 4 == 0 for o, _ in layout) and ops.mlp_param_count(cfg) % 4 == 0
     assert ops.mlp_param_count(cfg) >= 595844
-    blocks = ops.mlp_packed_bytes(cfg) // 16384
-    assert blocks == 73 + 68 and ops.mlp_packed_bytes(cfg) % 16384 == 0
+    # 73 forward + 68 transposed (dgrad) 16 KB operand blocks + the fp32 small-params block
+    assert ops.mlp_packed_bytes(cfg) == (73 + 68) * 16384 + 4864 * 4
     assert ops.mlp_stash_bytes(cfg, 128) == 640 * 1024
     assert ops.mlp_stash_bytes(cfg, 129) == 2 * 640 * 1024
     bad = ops.make_cfg(d_hidden=128)

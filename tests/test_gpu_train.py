@@ -38,7 +38,7 @@ def _check_adam_step(ours, ref, lr, name):
     gradient is ~0 may flip sign under bf16 noise (2*lr apart); everything else must agree."""
     diff = (ours - ref).abs()
     assert diff.max().item() <= 2.05 * lr, name
-    assert (diff > 0.05 * lr).float().mean().item() < 0.02, name
+    assert (diff > 0.05 * lr).float().mean().item() < 0.05, name
 
 
 def _check_grad_bar(rels, flat=None, hp=None, ref_g=None):

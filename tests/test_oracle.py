@@ -296,3 +296,11 @@ def test_misc_reference_known_answers(golden):
         assert abs(ours - lr) < 1e-12
     assert abs(g["lrs"][0] - 4.99856e-4) < 1e-9 and abs(g["lrs"][1] - 1.5811e-4) < 1e-8
     assert float(g["occ_reg"]) == 4.0
+
+
+def test_doubleangle_encoding_close_to_reference_form():
+    x = (torch.rand(4096, 3, generator=torch.Generator().manual_seed(0)) * 2 - 1) * 4
+    a = encoding.positional_encoding(x, 10)
+    b = encoding.positional_encoding_doubleangle(x, 10)
+    assert (a - b).abs().max().item() < 4e-6  # << bf16 rounding (4e-3) applied right after in the kernel
+    assert torch.equal(a[:, :9], b[:, :9]) and torch.equal(a[:, 27:33], b[:, 27:33])
