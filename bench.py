@@ -177,6 +177,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     ops.require_device(local)
     W_ = max(3, args.warmup)
@@ -310,6 +311,35 @@ def main():
                   "mlp_fwd_frac_of_bf16_peak": ((n_chunks * chunk * (N_COARSE + N_COARSE + N_FINE) * F_FWD)
                                                 / (fwd_ms / 1e3) / 1e12 / pk["tf_sus"]) if fwd_ms > 0 else None}
 
+    # ---- compositing kernel at render scale (HBM roofline of kernel (4); SURVEY.md §7 "hard parts":
+    #      at training sizes it is launch-latency bound and L2 resident)
+    comp = None
+    if rank == 0:
+        Rc, Sc_ = 262144, N_COARSE + N_FINE
+        gcomp = torch.Generator(device=dev).manual_seed(0)
+        raw = torch.rand(Rc, Sc_, 4, device=dev, generator=gcomp)
+        e_ = torch.sort(2 + 4 * torch.rand(Rc, Sc_ + 1, device=dev, generator=gcomp), -1).values
+        ts_, te_ = e_[:, :-1].contiguous(), e_[:, 1:].contiguous()
+        d_rgb_ = torch.rand(Rc, 3, device=dev, generator=gcomp)
+        bk_ = torch.ones(3, device=dev)
+        for _ in range(3):
+            ops.composite_forward(raw, ts_, te_, bkgd=bk_)
+            ops.composite_backward(raw, ts_, te_, d_rgb_, bkgd=bk_)
+        torch.cuda.synchronize()
+        ops.profile_enable(True)
+        for _ in range(10):
+            ops.composite_forward(raw, ts_, te_, bkgd=bk_)   # 1.4 GB in + out per launch >> L2
+            ops.composite_backward(raw, ts_, te_, d_rgb_, bkgd=bk_)
+        cprof = ops.profile_read()
+        ops.profile_enable(False)
+        pk_ = peaks()
+        f_ms, b_ms = cprof["composite_fwd"][0] / 10, cprof["composite_bwd"][0] / 10
+        f_bytes, b_bytes = Rc * (28 * Sc_ + 20), Rc * (40 * Sc_ + 40)  # bwd recomputes weights: 24 B in + 16 B out / sample
+        comp = {"rays": Rc, "samples_per_ray": Sc_, "bound": "hbm", "peak": pk_["hbm"], "unit": "GB/s",
+                "fwd": {"ms": f_ms, "achieved": f_bytes / f_ms / 1e6, "frac": f_bytes / f_ms / 1e6 / pk_["hbm"]},
+                "bwd": {"ms": b_ms, "achieved": b_bytes / b_ms / 1e6, "frac": b_bytes / b_ms / 1e6 / pk_["hbm"]}}
+        del raw, e_, ts_, te_
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -344,7 +374,7 @@ def main():
             "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e / Ke},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": base, "render": render,
+            "gpu_launches": launches, "roofline": roofline, "roofline_compositing": comp, "cpu_baseline": base, "render": render,
             "clocks": sampler.summary(), "final_loss": final_loss,
             "mlp_model_flops_per_ray": (N_COARSE + N_COARSE + N_FINE) * F_TRAIN}
     print(json.dumps(line))

@@ -19,12 +19,13 @@ import torch
 from . import ops
 from ._lib import FsnerfError
 from .core.models import NeRF, freq_mask
+from .parallel import allreduce_gradients, loss_grad_scale
 
 
 class HotPath:
     def __init__(self, n_coarse=64, n_fine=128, near=2.0, far=6.0, white_bkgd=True, device="cuda",
                  n_layers=8, d_hidden=256, skip=(4,), n_freqs=10, n_freqs_dir=4, log_space=True,
-                 seed=42, lr=5e-4, process_group=None):
+                 seed=42, lr=5e-4, process_group=None, world_size=None):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise FsnerfError("HotPath: CUDA device required (no CPU path)")
@@ -42,7 +43,7 @@ class HotPath:
         # seed-42 construction exactly like the reference (src/run-nerf.py:35-36,65-80);
         # the fine network, which the reference does not have, continues the same RNG stream
         self.params = torch.zeros(n_nets * self.n_net, device=self.device)
-        with torch.random.fork_rng():
+        with torch.random.fork_rng(devices=[]):  # weights are initialised on the CPU
             torch.manual_seed(seed)
             for i in range(n_nets):
                 net = NeRF(3, 3, n_layers, d_hidden, list(skip), **kw)
@@ -56,8 +57,11 @@ class HotPath:
         self.step = 0
         self.lr = lr
         self.pg = process_group
-        self.world = torch.distributed.get_world_size(process_group) if process_group is not None or (
-            torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
+        if world_size is not None:
+            self.world = int(world_size)
+        else:
+            self.world = torch.distributed.get_world_size(process_group) if process_group is not None or (
+                torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
         self.loss_sums = torch.zeros(2, device=self.device)
         self.mask_pos = self.mask_dir = None
         self._buf = {}
@@ -152,7 +156,7 @@ class HotPath:
         o = self._forward(rays_o, rays_d, u_strat, u_pdf, train=True)
         self.loss_sums.zero_()
         self.grads.zero_()
-        scale = 1.0 / (3.0 * G)  # F.mse_loss 'mean' over the GLOBAL batch (src/run-nerf.py:256)
+        scale = loss_grad_scale(G)  # F.mse_loss 'mean' over the GLOBAL batch (src/run-nerf.py:256)
         d_rgb_c = ops.mse_loss_grad(o["rgb_c"], rgb_gt, scale, self.loss_sums[0:1])
         d_raw_c, _ = ops.composite_backward(o["raw_c"].view(R, self.n_coarse, 4), o["ts_c"], o["te_c"], d_rgb_c,
                                             bkgd=self.bkgd)
@@ -171,7 +175,7 @@ class HotPath:
             self.launches += 2 + 3
         if self.world > 1:
             # the path's one real exchange: SUM of the flat fp32 gradient (both nets)
-            torch.distributed.all_reduce(self.grads, group=self.pg)
+            allreduce_gradients(self.grads, self.pg)
         if apply_update:
             self.step += 1
             ops.adam_step(self.params, self.grads, self.m, self.v, self.lr if lr is None else lr, self.step)

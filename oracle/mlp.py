@@ -20,7 +20,7 @@ def init_state_dict(n_layers=8, d_hidden=256, skip=(4,), n_freqs=10,
     d_pe = d_pos * (1 + 2 * n_freqs)
     d_de = d_dir * (1 + 2 * n_freqs_dir)
     sd = {}
-    with torch.random.fork_rng():
+    with torch.random.fork_rng(devices=[]):
         torch.manual_seed(seed)
 
         def linear(name, n_in, n_out):
