@@ -1,5 +1,6 @@
 """CPU tests: the oracle against the reference-generated golden fixtures and
 closed-form known answers."""
+import pytest
 import numpy as np
 import torch
 
@@ -304,3 +305,24 @@ def test_doubleangle_encoding_close_to_reference_form():
     b = encoding.positional_encoding_doubleangle(x, 10)
     assert (a - b).abs().max().item() < 4e-6  # << bf16 rounding (4e-3) applied right after in the kernel
     assert torch.equal(a[:, :9], b[:, :9]) and torch.equal(a[:, 27:33], b[:, 27:33])
+
+
+def test_scheduler_mirror_matches_reference_values(golden):
+    """fsnerf_b200.core.scheduler (row a10) against values produced by the reference's
+    core.scheduler.ExponentialDecay (tests/golden/reference_misc.npz, oracle/gen_golden.py)"""
+    from fsnerf_b200.core.scheduler import Constant, ExponentialDecay, lr_at
+    g = golden("reference_misc.npz")
+    opt = torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], lr=5e-4)
+    sch = ExponentialDecay(opt, 8000, 5e-4, r=0.1)
+    seen = {}
+    for t in range(1, 8100):
+        sch.step()
+        seen[t] = opt.param_groups[0]["lr"]
+    for t, lr in zip(g["lr_steps"], g["lrs"]):
+        assert abs(seen[int(t)] - lr) < 1e-12 and abs(lr_at(int(t), 8000, 5e-4, 0.1) - lr) < 1e-12
+    assert seen[8099] == 5e-4 * 0.1 and sch.lrf == 5e-4 * 0.1
+    c = Constant(opt, 10, 3e-4)
+    c.step()
+    assert opt.param_groups[0]["lr"] == 3e-4
+    with pytest.raises(ValueError):
+        Constant(opt, 10, -1.0)
