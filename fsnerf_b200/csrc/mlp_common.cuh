@@ -81,4 +81,10 @@ struct MlpProgram {
 // Build the program from the architecture; returns 0 or FSNERF_ERR_*.
 int build_program(const fsnerf_net_cfg* cfg, MlpProgram* prog);
 
+// second-generation forward (mlp_fwd2.cu): activations resident in tensor memory
+int mlp_forward_v2(const MlpProgram& P, const void* packed, int64_t n_samples, int samples_per_ray,
+                   const float* rays_o, const float* rays_d, const float* t_starts, const float* t_ends,
+                   const float* x, const float* dirs, const float* mask_pos, const float* mask_dir,
+                   int density_only, float* out, void* stash, void* stream);
+
 }  // namespace fs

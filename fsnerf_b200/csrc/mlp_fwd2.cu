@@ -1,0 +1,454 @@
+// Kernels (2)+(3), second generation: the fused NeRF MLP forward with the
+// activations resident in TENSOR MEMORY (reference: src/core/models.py:111-143
+// evaluated in the closures of src/render/rendering.py:58-84).
+//
+// One persistent CTA per SM (480 threads), one 128-sample tile at a time:
+//   warps 0..7   epilogue: warp w owns TMEM lanes 32*(w&3).. (sample rows) and the
+//                column half (w>>2) of every 64-feature chunk.  TMEM -> regs -> bias +
+//                ReLU -> bf16x2 -> written back IN PLACE over the fp32 columns just
+//                consumed: the next layer's A operand never touches shared memory.
+//                Each finished chunk is handed to the MMA warp (mbarrier per chunk), so
+//                layer l+1's MMAs on chunk 0 run while chunks 1..3 are still converted.
+//   warps 8..11  encoders: ray -> position -> masked sin/cos encoding of position and
+//                view direction into two [128 x 64] SW128 smem tiles, one tile ahead.
+//   warp 12      MMA issuer: tcgen05.mma M=128 N=256 K=16 kind::f16; A from TMEM
+//                (hidden chunks) or smem (encodings), B from the smem weight ring;
+//                the two 256-column TMEM regions alternate accumulator / operand role.
+//   warps 13..14 weight producers: 32 KB [256 x 64] operand stages L2 -> smem with
+//                cp.async.bulk; two issuing warps because bulk copies issued by one
+//                thread do not overlap (tools/l2_bench.cu).
+// Training (kTrain): every A image (SW128 byte image, the format dgrad / wgrad load
+// back) is also staged through smem per 32-row slab and bulk-stored to the stash.
+#include <stdlib.h>
+#include "common.cuh"
+#include "mlp_common.cuh"
+#include "mlp_encode.cuh"
+
+namespace fs {
+namespace {
+
+constexpr int kEpiWarps = 8;
+constexpr int kEncWarps = 4;
+constexpr int kProdWarps = 2;
+constexpr int kWarpEnc0 = kEpiWarps;               // 8
+constexpr int kWarpMma = kEpiWarps + kEncWarps;    // 12
+constexpr int kWarpProd0 = kWarpMma + 1;           // 13
+constexpr int kThreads2 = (kWarpProd0 + kProdWarps) * 32;  // 480
+constexpr int kStageBytes = 2 * kBlockBytes;       // [256 x 64] bf16
+constexpr int kSlabBytes2 = 32 * 128;              // 32 rows of one chunk image
+constexpr int kStageBufs = 3;                      // staging buffers per lane quarter
+constexpr int kTmemCols2 = 512;
+
+template <bool kTrain> __host__ __device__ constexpr int n_stages() { return kTrain ? 4 : 5; }
+template <bool kTrain> struct Smem {
+  static constexpr int ring = 0;
+  static constexpr int aux_pos = ring + n_stages<kTrain>() * kStageBytes;
+  static constexpr int aux_dir = aux_pos + kChunkBytes;
+  static constexpr int staging = aux_dir + kChunkBytes;
+  static constexpr int exch = staging + (kTrain ? 4 * kStageBufs * kSlabBytes2 : 0);
+  static constexpr int bars = exch + kTileM * 16;
+  static constexpr int total = bars + 256;
+};
+
+__constant__ float c_small2[kSmallFloats];
+
+#define FS_TRACE2(slot, g_, k_)                                                             \
+  do {                                                                                      \
+    if (args.trace && blockIdx.x == 0 && (slot) < 4)                                        \
+      args.trace[((slot) * 16 + (g_)) * 8 + (k_)] = clock64();                              \
+  } while (0)
+
+struct Fwd2Args {
+  long long* trace;
+  const uint8_t* packed;
+  int64_t n_samples;
+  int samples_per_ray;
+  const float* rays_o;
+  const float* rays_d;
+  const float* t_starts;
+  const float* t_ends;
+  const float* x;
+  const float* dirs;
+  const float* mask_pos;
+  const float* mask_dir;
+  int density_only;
+  float* out;
+  uint8_t* stash;
+};
+
+template <bool kTrain>
+__global__ void __launch_bounds__(kThreads2, 1)
+mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ Fwd2Args args) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  using S = Smem<kTrain>;
+  constexpr int kStages = n_stages<kTrain>();
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_w_full = sbase + S::bars;               // [kStages]
+  const uint32_t bar_w_empty = bar_w_full + 8 * kStages;     // [kStages]
+  const uint32_t bar_a_ready = bar_w_empty + 8 * kStages;    // [4]
+  const uint32_t bar_acc_full = bar_a_ready + 8 * 4;         // [2]
+  const uint32_t bar_pos_full = bar_acc_full + 8 * 2;
+  const uint32_t bar_pos_empty = bar_pos_full + 8;
+  const uint32_t bar_dir_full = bar_pos_empty + 8;
+  const uint32_t bar_dir_empty = bar_dir_full + 8;
+  const uint32_t tmem_slot = bar_dir_empty + 8;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + S::bars + 8 * (2 * kStages + 4 + 2 + 4));
+  float4* exch = reinterpret_cast<float4*>(smem + S::exch);
+
+  const int n_gemm = args.density_only ? prog.n_hidden : prog.n_gemm;
+  int last_pos_user = 0;  // last hidden layer whose MMA reads the position encoding
+  for (int g = 0; g < prog.n_hidden; ++g)
+    if (prog.layer[g].use_aux) last_pos_user = g;
+  const int64_t n_tiles = (args.n_samples + kTileM - 1) / kTileM;
+
+  if ((sbase & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("fsnerf: dynamic smem base not 1024B aligned (%u)\n", sbase);
+    __trap();
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_w_full + 8 * s, 1);
+      mbar_init(bar_w_empty + 8 * s, 1);
+    }
+    for (int c = 0; c < 4; ++c) mbar_init(bar_a_ready + 8 * c, kEpiWarps);
+    mbar_init(bar_acc_full, 1);
+    mbar_init(bar_acc_full + 8, 1);
+    mbar_init(bar_pos_full, kEncWarps);
+    mbar_init(bar_pos_empty, 1);
+    mbar_init(bar_dir_full, kEncWarps);
+    mbar_init(bar_dir_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == kWarpMma) {
+    tmem_alloc(tmem_slot, kTmemCols2);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp >= kWarpProd0) {
+    // ------------------------------------------------ weight producers
+    const int me = warp - kWarpProd0;
+    uint32_t cnt = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int g = 0; g < n_gemm; ++g) {
+        const GemmLayer& L = prog.layer[g];
+        const int nchunks = L.n_act_chunks + L.use_aux;
+        const uint32_t bytes = (uint32_t)L.n_halves * kBlockBytes;
+        for (int c = 0; c < nchunks; ++c, ++cnt) {
+          if ((int)(cnt % kProdWarps) != me) continue;
+          const uint32_t stage = cnt % kStages, phase = (cnt / kStages) & 1;
+          mbar_wait(bar_w_empty + 8 * stage, phase ^ 1);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(bar_w_full + 8 * stage, bytes);
+            bulk_g2s(sbase + S::ring + stage * kStageBytes,
+                     args.packed + (size_t)(L.first_block + c * L.n_halves) * kBlockBytes, bytes,
+                     bar_w_full + 8 * stage);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == kWarpMma) {
+    // ------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc256 = umma_idesc_bf16(128, 256, 0, 0);
+    constexpr uint32_t idesc128 = umma_idesc_bf16(128, 128, 0, 0);
+    uint32_t cnt = 0, a_cnt = 0, acc_cnt[2] = {0, 0};
+    uint32_t titer = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
+      for (int g = 0; g < n_gemm; ++g) {
+        const GemmLayer& L = prog.layer[g];
+        const uint32_t d_col = tmem_base + (uint32_t)(g & 1) * 256u;
+        const uint32_t a_col = tmem_base + (uint32_t)((g + 1) & 1) * 256u;
+        const uint32_t idesc = (L.n_halves == 2) ? idesc256 : idesc128;
+        uint32_t accum = 0;
+        if (lane == 0) FS_TRACE2(titer, g, 0);
+        for (int c = 0; c < L.n_act_chunks; ++c, ++cnt) {
+          mbar_wait(bar_a_ready + 8 * c, a_cnt & 1);
+          const uint32_t stage = cnt % kStages, phase = (cnt / kStages) & 1;
+          mbar_wait(bar_w_full + 8 * stage, phase);
+          tc_fence_after();
+          if (lane == 0) {
+            if (c == 0) FS_TRACE2(titer, g, 1);
+            const uint32_t b_tile = sbase + S::ring + stage * kStageBytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              // chunk c: features [0,32) packed at columns 64c.., [32,64) at 64c+32..
+              umma_bf16_ts(d_col, a_col + 64 * c + 32 * (k >> 1) + 8 * (k & 1),
+                           umma_desc_sw128(b_tile + k * 32, 16, 1024), idesc, accum);
+              accum = 1;
+            }
+            umma_commit(bar_w_empty + 8 * stage);
+          }
+          __syncwarp();
+        }
+        if (L.n_act_chunks) ++a_cnt;
+        if (L.use_aux) {
+          const bool is_dir = (L.epi == EPI_BRANCH);
+          mbar_wait(is_dir ? bar_dir_full : bar_pos_full, titer & 1);
+          const uint32_t stage = cnt % kStages, phase = (cnt / kStages) & 1;
+          mbar_wait(bar_w_full + 8 * stage, phase);
+          tc_fence_after();
+          if (lane == 0) {
+            if (L.n_act_chunks == 0) FS_TRACE2(titer, g, 1);
+            const uint32_t a_tile = sbase + (is_dir ? S::aux_dir : S::aux_pos);
+            const uint32_t b_tile = sbase + S::ring + stage * kStageBytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16_ss(d_col, umma_desc_sw128(a_tile + k * 32, 16, 1024),
+                           umma_desc_sw128(b_tile + k * 32, 16, 1024), idesc, accum);
+              accum = 1;
+            }
+            umma_commit(bar_w_empty + 8 * stage);
+            if (is_dir) umma_commit(bar_dir_empty);
+            else if (g == last_pos_user) umma_commit(bar_pos_empty);
+          }
+          __syncwarp();
+          ++cnt;
+        }
+        if (lane == 0) {
+          umma_commit(bar_acc_full + 8 * (g & 1));
+          FS_TRACE2(titer, g, 2);
+        }
+        __syncwarp();
+        ++acc_cnt[g & 1];
+      }
+      // the next tile's first layer overwrites region 0, which the last layer still
+      // reads as its A operand: let the tensor pipe drain first
+      const int gl = n_gemm - 1;
+      mbar_wait(bar_acc_full + 8 * (gl & 1), (acc_cnt[gl & 1] - 1) & 1);
+    }
+  } else if (warp >= kWarpEnc0) {
+    // ------------------------------------------------ encoders (thread = sample row)
+    const int row = (warp - kWarpEnc0) * 32 + lane;
+    uint32_t titer = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
+      const int64_t p = tile * kTileM + row;
+      const bool valid = p < args.n_samples;
+      float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
+      if (valid) {
+        if (args.x) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) pos[a] = args.x[p * 3 + a];
+          if (args.dirs) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) dir[a] = args.dirs[p * 3 + a];
+          }
+        } else {
+          const int64_t ray = p / args.samples_per_ray;
+          // reference: src/render/rendering.py:79  x = o + d*(ts+te)/2
+          const float tm = (args.t_starts[p] + args.t_ends[p]) / 2.0f;
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            dir[a] = args.rays_d[ray * 3 + a];
+            pos[a] = args.rays_o[ray * 3 + a] + dir[a] * tm;
+          }
+        }
+      }
+      uint8_t* stash_tile = kTrain ? args.stash + (size_t)tile * prog.stash_tile_bytes : nullptr;
+      if (kTrain) {  // this warp's previous slab stores must have finished reading the tiles
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+      }
+      mbar_wait(bar_pos_empty, (titer & 1) ^ 1);
+      encode_row(pos, prog.n_freqs_pos, prog.freq_pos, prog.pow2_freqs != 0, args.mask_pos,
+                 sbase + S::aux_pos, row);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_pos_full);
+        if (kTrain) {
+          const int slab = (warp - kWarpEnc0) * kSlabBytes2;
+          bulk_s2g(stash_tile + prog.stash_aux_pos_off + slab, sbase + S::aux_pos + slab, kSlabBytes2);
+          bulk_commit();
+        }
+      }
+      if (!args.density_only) {
+        mbar_wait(bar_dir_empty, (titer & 1) ^ 1);
+        encode_row(dir, prog.n_freqs_dir, prog.freq_dir, prog.pow2_freqs != 0, args.mask_dir,
+                   sbase + S::aux_dir, row);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar_dir_full);
+          if (kTrain) {
+            const int slab = (warp - kWarpEnc0) * kSlabBytes2;
+            bulk_s2g(stash_tile + prog.stash_aux_dir_off + slab, sbase + S::aux_dir + slab, kSlabBytes2);
+            bulk_commit();
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (kTrain && lane == 0) bulk_wait0();
+  } else {
+    // ------------------------------------------------ epilogue
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t stage_base = sbase + S::staging + quarter * (kStageBufs * kSlabBytes2);
+    const bool issuer = kTrain && half == 0 && lane == 0;
+    uint32_t acc_phase[2] = {0, 0};
+    uint32_t n_staged = 0;
+    uint32_t titer = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
+      const int64_t p = tile * kTileM + row;
+      const bool valid = p < args.n_samples;
+      uint8_t* stash_tile = kTrain ? args.stash + (size_t)tile * prog.stash_tile_bytes : nullptr;
+      float sigma = 0.f;
+      for (int g = 0; g < n_gemm; ++g) {
+        const GemmLayer& L = prog.layer[g];
+        const int r = g & 1;
+        const uint32_t region = tmem_lane + (uint32_t)r * 256u;
+        const bool last = (g == n_gemm - 1);
+        const int epi = L.epi;
+        const int nchunk = L.n_halves * 2;
+        if (threadIdx.x == 0) FS_TRACE2(titer, g, 3);
+        mbar_wait(bar_acc_full + 8 * r, acc_phase[r]);
+        acc_phase[r] ^= 1;
+        tc_fence_after();
+        if (threadIdx.x == 0) FS_TRACE2(titer, g, 4);
+        float part[3] = {0.f, 0.f, 0.f};
+        float sig_part = 0.f;
+        uint32_t v[2][32];
+        tmem_ld32(region + 32 * half, v[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < nchunk) {
+            const int c0 = 64 * c + 32 * half;  // first feature handled by this thread
+            tmem_ld_wait();
+            if (c + 1 < nchunk) tmem_ld32(region + 64 * (c + 1) + 32 * half, v[(c + 1) & 1]);
+            const uint32_t(&vc)[32] = v[c & 1];
+            const float2* __restrict__ cb2 =
+                reinterpret_cast<const float2*>(c_small2 + kSmallBias + g * 256 + c0);
+            uint32_t w[16];
+            if (epi == EPI_RELU || epi == EPI_CONN) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float2 b = cb2[i];
+                float s0, s1;
+                add_f32x2(s0, s1, __uint_as_float(vc[2 * i]), __uint_as_float(vc[2 * i + 1]), b.x, b.y);
+                w[i] = (epi == EPI_RELU) ? pack_bf16x2_relu(s0, s1) : pack_bf16x2(s0, s1);
+              }
+            } else {
+              float h[32];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float2 b = cb2[i];
+                h[2 * i] = fmaxf(__uint_as_float(vc[2 * i]) + b.x, 0.f);
+                h[2 * i + 1] = fmaxf(__uint_as_float(vc[2 * i + 1]) + b.y, 0.f);
+                w[i] = pack_bf16x2(h[2 * i], h[2 * i + 1]);
+              }
+              if (epi == EPI_RELU_SIGMA) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sig_part = fmaf(h[i], c_small2[kSmallSigmaW + c0 + i], sig_part);
+              } else {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i)
+                    part[ch] = fmaf(h[i], c_small2[kSmallRgbW + ch * 128 + c0 + i], part[ch]);
+                }
+              }
+            }
+            if (!last) {
+              // bf16 pairs back into TMEM over the first 16 of the 32 fp32 columns just read
+              tmem_st16(region + c0, w);
+              tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_a_ready + 8 * c);
+            }
+            if (kTrain) {
+              // SW128 image slab of this quarter's 32 rows of chunk c -> stash
+              const uint32_t buf = stage_base + (n_staged % kStageBufs) * kSlabBytes2;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                st_shared_v4(buf + lane * 128 + (((uint32_t)(4 * half + j) ^ (uint32_t)(lane & 7)) << 4),
+                             w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+              fence_proxy_async_smem();
+              if (issuer) bulk_wait_read1();  // slabs older than the previous one have been read
+              named_bar_sync(1 + quarter, 64);
+              if (issuer) {
+                bulk_s2g(stash_tile + L.stash_off + c * kChunkBytes + quarter * kSlabBytes2, buf, kSlabBytes2);
+                bulk_commit();
+              }
+              ++n_staged;
+            }
+          }
+        }
+        if (threadIdx.x == 0) FS_TRACE2(titer, g, 5);
+        if (epi == EPI_RELU_SIGMA) {
+          if (half == 1) exch[row].w = sig_part;
+          named_bar_sync(1 + quarter, 64);
+          if (half == 0) sigma = sig_part + exch[row].w + c_small2[kSmallSigmaB];
+          if (last && half == 0 && valid) args.out[p] = sigma;  // density_only
+        } else if (epi == EPI_BRANCH) {
+          if (half == 1) {
+            exch[row].x = part[0]; exch[row].y = part[1]; exch[row].z = part[2];
+          }
+          named_bar_sync(1 + quarter, 64);
+          if (half == 0 && valid) {
+            const float4 e = exch[row];
+            const float z0 = part[0] + e.x + c_small2[kSmallRgbB + 0];
+            const float z1 = part[1] + e.y + c_small2[kSmallRgbB + 1];
+            const float z2 = part[2] + e.z + c_small2[kSmallRgbB + 2];
+            reinterpret_cast<float4*>(args.out)[p] =
+                make_float4(1.0f / (1.0f + expf(-z0)), 1.0f / (1.0f + expf(-z1)), 1.0f / (1.0f + expf(-z2)), sigma);
+          }
+        }
+      }
+    }
+    if (issuer) bulk_wait0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWarpMma) tmem_dealloc(tmem_base, kTmemCols2);
+}
+
+}  // namespace
+
+int mlp_forward_v2(const MlpProgram& P, const void* packed, int64_t n_samples, int samples_per_ray,
+                   const float* rays_o, const float* rays_d, const float* t_starts, const float* t_ends,
+                   const float* x, const float* dirs, const float* mask_pos, const float* mask_dir,
+                   int density_only, float* out, void* stash, void* stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e1 = cudaFuncSetAttribute(mlp_fwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Smem<false>::total);
+    cudaError_t e2 = cudaFuncSetAttribute(mlp_fwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Smem<true>::total);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      fsnerf_set_error("mlp_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+      return FSNERF_ERR_CUDA;
+    }
+    configured = true;
+  }
+  Fwd2Args a;
+  a.trace = reinterpret_cast<long long*>(fsnerf_debug_trace_ptr());
+  a.packed = reinterpret_cast<const uint8_t*>(packed);
+  a.n_samples = n_samples; a.samples_per_ray = samples_per_ray;
+  a.rays_o = rays_o; a.rays_d = rays_d; a.t_starts = t_starts; a.t_ends = t_ends;
+  a.x = x; a.dirs = dirs; a.mask_pos = mask_pos; a.mask_dir = mask_dir;
+  a.density_only = density_only; a.out = out; a.stash = reinterpret_cast<uint8_t*>(stash);
+  const int64_t n_tiles = (n_samples + kTileM - 1) / kTileM;
+  const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_small2, a.packed + P.small_off, kSmallFloats * sizeof(float), 0,
+                                          cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    fsnerf_set_error("mlp_forward: constant upload: %s", cudaGetErrorString(e));
+    return FSNERF_ERR_CUDA;
+  }
+  FsProfScope prof_(stash ? "mlp_fwd_train" : "mlp_fwd", stream);
+  if (stash)
+    mlp_fwd2_kernel<true><<<grid, kThreads2, Smem<true>::total, (cudaStream_t)stream>>>(P, a);
+  else
+    mlp_fwd2_kernel<false><<<grid, kThreads2, Smem<false>::total, (cudaStream_t)stream>>>(P, a);
+  return fsnerf_check_launch("mlp_forward");
+}
+
+}  // namespace fs
