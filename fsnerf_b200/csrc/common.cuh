@@ -55,14 +55,17 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
 }
+// The suspend-time hint lets the hardware park the warp until the phase completes (or the
+// hint expires) instead of returning quickly: a CTA with a dozen role warps blocked in
+// un-hinted try_wait loops floods the SM's MIO queue and slows the MMA-issuing warp ~2x.
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
@@ -74,6 +77,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > (1u << 24)) {
       printf("fsnerf: mbarrier timeout blk %d thr %d bar %u parity %u\n", blockIdx.x, threadIdx.x,
              bar, parity);
+      __trap();
+    }
+  }
+}
+
+// Same, for a warp that must stay provably CONVERGED (the MMA issuer): the loop exit is a
+// warp vote, so the compiler's divergence analysis keeps everything downstream uniform
+// (operands of the tcgen05 instructions then live in uniform registers).
+__device__ __forceinline__ void mbar_wait_converged(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+    if (++spins > (1u << 24)) {
+      if ((threadIdx.x & 31) == 0)
+        printf("fsnerf: mbarrier timeout blk %d thr %d bar %u parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();
     }
   }
@@ -187,6 +204,89 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Converged-issue forms: executed by ALL lanes of the issuing warp with warp-uniform
+// operands (they stay in uniform registers: no R2UR/ELECT waterfall per instruction) and
+// a per-lane guard that is true for one lane only.  Measured (tools/mma_bench.cu):
+// 128.0 cycles per M=128 N=256 K=16 MMA vs 138 issue-bound cycles from a lane-0 branch.
+__device__ __forceinline__ void umma_bf16_ts_conv(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b,
+                                                  uint32_t idesc, uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 e, %5, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_conv(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                  uint32_t idesc, uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 e, %5, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+// Two MMAs with two NON-BLOCKING mbarrier probes slotted between them (converged issue).
+// The tensor pipe accepts the next MMA only when the previous one is (nearly) done and has
+// < 100 cycles of slack before it idles (tools/mma_bench.cu), so everything the issuing warp
+// must do for the NEXT chunk (iterator advance, descriptors, readiness tests) is placed
+// between the MMA issues of the current chunk, never between chunks.
+template <bool kATmem>
+__device__ __forceinline__ void umma2_probe(uint32_t tmem_d, uint64_t a0, uint64_t a1, uint64_t b0, uint64_t b1,
+                                            uint32_t idesc, uint32_t issue, uint32_t bar0, uint32_t par0,
+                                            uint32_t bar1, uint32_t par1, uint32_t& ok0, uint32_t& ok1) {
+  if (kATmem) {
+    asm volatile(
+        "{\n\t.reg .pred e, t, q0, q1;\n\t"
+        "setp.ne.b32 e, %8, 0;\n\t"
+        "setp.eq.b32 t, %8, %8;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%2], [%3], %5, %7, t;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q0, [%9], %10;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q1, [%11], %12;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%2], [%4], %6, %7, t;\n\t"
+        "selp.u32 %0, 1, 0, q0;\n\t"
+        "selp.u32 %1, 1, 0, q1;\n\t}"
+        : "=r"(ok0), "=r"(ok1)
+        : "r"(tmem_d), "r"((uint32_t)a0), "r"((uint32_t)a1), "l"(b0), "l"(b1), "r"(idesc), "r"(issue),
+          "r"(bar0), "r"(par0), "r"(bar1), "r"(par1)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred e, t, q0, q1;\n\t"
+        "setp.ne.b32 e, %8, 0;\n\t"
+        "setp.eq.b32 t, %8, %8;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%2], %3, %5, %7, t;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q0, [%9], %10;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q1, [%11], %12;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%2], %4, %6, %7, t;\n\t"
+        "selp.u32 %0, 1, 0, q0;\n\t"
+        "selp.u32 %1, 1, 0, q1;\n\t}"
+        : "=r"(ok0), "=r"(ok1)
+        : "r"(tmem_d), "l"(a0), "l"(a1), "l"(b0), "l"(b1), "r"(idesc), "r"(issue),
+          "r"(bar0), "r"(par0), "r"(bar1), "r"(par1)
+        : "memory");
+  }
+}
+// low word of a SWIZZLE_128B K-major descriptor (start address, LBO = 16 B) and the
+// constant high word (SBO = 1024 B, version 1, layout SW128): desc = hi:lo, and advancing
+// by 32 bytes along K adds 2 to the low word
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) {
+  return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);
+}
+constexpr uint32_t kUmmaDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint64_t umma_desc_from_lo(uint32_t lo) {
+  return ((uint64_t)kUmmaDescHiSw128 << 32) | lo;
+}
+__device__ __forceinline__ void umma_commit_conv(uint32_t bar, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "setp.ne.b32 e, %1, 0;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar),
+      "r"(issue)
       : "memory");
 }
 // registers -> TMEM: thread i of the warp writes lane (taddr.lane + i), 16 consecutive columns

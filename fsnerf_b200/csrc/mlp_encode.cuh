@@ -6,10 +6,14 @@
 
 namespace fs {
 
+// out of line on purpose: sincosf's argument reduction is ~150 instructions and the fused
+// MLP kernels must keep their hot loops instruction-cache resident
+static __device__ __noinline__ void sincos_acc(float x, float* sn, float* cs) { sincosf(x, sn, cs); }
+
 // sin/cos encoding of v[3] -> 64 bf16 channels (zero padded) into row `row` of a
 // [128 x 64] SW128 tile at smem address `tile`.
 // reference: src/core/models.py:43-50 (channel order x, sin(f0 x), cos(f0 x), ...)
-__device__ __forceinline__ void encode_row(const float v[3], int n_freqs, const float* freqs, bool pow2,
+static __device__ __noinline__ void encode_row(const float v[3], int n_freqs, const float* freqs, bool pow2,
                                            const float* __restrict__ mask, uint32_t tile, int row) {
   float ch[64];
 #pragma unroll
@@ -26,7 +30,7 @@ __device__ __forceinline__ void encode_row(const float v[3], int n_freqs, const 
       for (int k = 0; k < kMaxFreqs; ++k) {
         if (k < n_freqs) {
           if ((k & 3) == 0) {
-            sincosf(v[a] * freqs[k], &sn, &cs);
+            sincos_acc(v[a] * freqs[k], &sn, &cs);
           } else {
             const float s2 = 2.0f * sn * cs;
             cs = fmaf(-2.0f * sn, sn, 1.0f);
@@ -45,7 +49,7 @@ __device__ __forceinline__ void encode_row(const float v[3], int n_freqs, const 
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
           float sn, cs;
-          sincosf(v[a] * f, &sn, &cs);
+          sincos_acc(v[a] * f, &sn, &cs);
           ch[3 + 6 * k + a] = sn;
           ch[3 + 6 * k + 3 + a] = cs;
         }

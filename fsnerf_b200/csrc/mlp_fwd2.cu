@@ -31,13 +31,22 @@ constexpr int kEpiWarps = 8;
 constexpr int kEncWarps = 4;
 constexpr int kProdWarps = 2;
 constexpr int kWarpEnc0 = kEpiWarps;               // 8
-constexpr int kWarpMma = kEpiWarps + kEncWarps;    // 12
-constexpr int kWarpProd0 = kWarpMma + 1;           // 13
-constexpr int kThreads2 = (kWarpProd0 + kProdWarps) * 32;  // 480
+constexpr int kMmaWarps = 2;                       // MMA issuers, alternating K chunks
+constexpr int kWarpMma = kEpiWarps + kEncWarps;    // 12, 13
+constexpr int kWarpProd0 = kWarpMma + kMmaWarps;   // 14
+constexpr int kThreads2 = (kWarpProd0 + kProdWarps) * 32;  // 512
 constexpr int kStageBytes = 2 * kBlockBytes;       // [256 x 64] bf16
 constexpr int kSlabBytes2 = 32 * 128;              // 32 rows of one chunk image
 constexpr int kStageBufs = 3;                      // staging buffers per lane quarter
 constexpr int kTmemCols2 = 512;
+constexpr int kMaxLayers2 = 12;                    // GEMM layers whose biases fit the smem table
+constexpr int kMaxChunks2 = 64;                    // K chunks per tile in the MMA issue table
+// MMA issue table record flags
+constexpr uint32_t kRecDcol = 0x100u;              // accumulator region: TMEM column offset 0 / 256
+constexpr uint32_t kRecTmem = 1u << 16;            // A operand from tensor memory (else smem encoding tile)
+constexpr uint32_t kRecFirst = 1u << 17;           // first chunk of its layer: overwrite the accumulator
+constexpr uint32_t kRecParTile = 1u << 18;         // operand barrier completes once per tile
+constexpr uint32_t kRecParShift = 19;              // bit 19: parity of the consumer-layer index in the tile
 
 template <bool kTrain> __host__ __device__ constexpr int n_stages() { return kTrain ? 4 : 5; }
 template <bool kTrain> struct Smem {
@@ -46,8 +55,25 @@ template <bool kTrain> struct Smem {
   static constexpr int aux_dir = aux_pos + kChunkBytes;
   static constexpr int staging = aux_dir + kChunkBytes;
   static constexpr int exch = staging + (kTrain ? 4 * kStageBufs * kSlabBytes2 : 0);
-  static constexpr int bars = exch + kTileM * 16;
+  static constexpr int bias = exch + kTileM * 16;              // fp32 [kMaxLayers2][256]
+  static constexpr int heads = bias + kMaxLayers2 * 256 * 4;   // fp32 sigma_w[256], rgb_w[3][128]
+  static constexpr int bars = heads + 640 * 4;
   static constexpr int total = bars + 256;
+};
+
+// barrier block layout (byte offsets from Smem::bars)
+template <bool kTrain> struct Bars {
+  static constexpr int S = n_stages<kTrain>();
+  static constexpr int w_full = Smem<kTrain>::bars;
+  static constexpr int w_empty = w_full + 8 * S;
+  static constexpr int a_ready = w_empty + 8 * S;   // [4]
+  static constexpr int acc_full = a_ready + 8 * 4;  // [2]
+  static constexpr int pos_full = acc_full + 8 * 2;
+  static constexpr int pos_empty = pos_full + 8;
+  static constexpr int dir_full = pos_empty + 8;
+  static constexpr int dir_empty = dir_full + 8;
+  static constexpr int token = dir_empty + 8;       // [2] MMA issuers' hand-over
+  static constexpr int tmem_slot = token + 16;
 };
 
 __constant__ float c_small2[kSmallFloats];
@@ -57,6 +83,28 @@ __constant__ float c_small2[kSmallFloats];
     if (args.trace && blockIdx.x == 0 && (slot) < 4)                                        \
       args.trace[((slot) * 16 + (g_)) * 8 + (k_)] = clock64();                              \
   } while (0)
+
+// MMA issue table: one record per 64-wide K chunk of a tile, in consumption order (the
+// encoding chunk of a layer first).  Passed as a __grid_constant__ kernel parameter so the
+// issuing warp reads it with uniform loads: everything it feeds to tcgen05.mma stays in
+// uniform registers (a record fetched from shared memory costs an R2UR waterfall per MMA).
+struct IssueRec {
+  uint32_t flags;    // kRec* | layer << 24
+  uint32_t idesc;
+  uint32_t a0;       // TMEM column of the chunk's A operand, or byte offset of the smem encoding tile
+  uint32_t abar;     // smem byte offset of the operand-ready barrier
+  uint32_t xbar;     // smem byte offset of the "encoding tile free" barrier to commit (0: none)
+  uint32_t accbar;   // smem byte offset of the accumulator-full barrier to commit after the chunk (0: none)
+  uint32_t n_acc;    // how many times to commit it (the barrier expects 2 arrivals per layer, one per issuer)
+  uint32_t pad;
+};
+struct IssueTable {
+  int n;
+  uint32_t a_tile_odd;    // 1 if the number of TMEM-fed layers per tile is odd
+  uint32_t last_acc_off;  // accumulator-full barrier of the tile's last layer (smem byte offset)
+  uint32_t last_acc_n;    // layers per tile sharing that barrier
+  IssueRec rec[kMaxChunks2];
+};
 
 struct Fwd2Args {
   long long* trace;
@@ -78,23 +126,25 @@ struct Fwd2Args {
 
 template <bool kTrain>
 __global__ void __launch_bounds__(kThreads2, 1)
-mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ Fwd2Args args) {
+mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ Fwd2Args args,
+                const __grid_constant__ IssueTable tab) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using S = Smem<kTrain>;
   constexpr int kStages = n_stages<kTrain>();
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t bar_w_full = sbase + S::bars;               // [kStages]
-  const uint32_t bar_w_empty = bar_w_full + 8 * kStages;     // [kStages]
-  const uint32_t bar_a_ready = bar_w_empty + 8 * kStages;    // [4]
-  const uint32_t bar_acc_full = bar_a_ready + 8 * 4;         // [2]
-  const uint32_t bar_pos_full = bar_acc_full + 8 * 2;
-  const uint32_t bar_pos_empty = bar_pos_full + 8;
-  const uint32_t bar_dir_full = bar_pos_empty + 8;
-  const uint32_t bar_dir_empty = bar_dir_full + 8;
-  const uint32_t tmem_slot = bar_dir_empty + 8;
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem + S::bars + 8 * (2 * kStages + 4 + 2 + 4));
+  using B = Bars<kTrain>;
+  const uint32_t bar_w_full = sbase + B::w_full;       // [kStages]
+  const uint32_t bar_w_empty = sbase + B::w_empty;     // [kStages]
+  const uint32_t bar_a_ready = sbase + B::a_ready;     // [4]
+  const uint32_t bar_acc_full = sbase + B::acc_full;   // [2]
+  const uint32_t bar_pos_full = sbase + B::pos_full;
+  const uint32_t bar_pos_empty = sbase + B::pos_empty;
+  const uint32_t bar_dir_full = sbase + B::dir_full;
+  const uint32_t bar_dir_empty = sbase + B::dir_empty;
+  const uint32_t bar_token = sbase + B::token;         // [2]
+  const uint32_t tmem_slot = sbase + B::tmem_slot;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + B::tmem_slot);
   float4* exch = reinterpret_cast<float4*>(smem + S::exch);
 
   const int n_gemm = args.density_only ? prog.n_hidden : prog.n_gemm;
@@ -113,8 +163,10 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
       mbar_init(bar_w_empty + 8 * s, 1);
     }
     for (int c = 0; c < 4; ++c) mbar_init(bar_a_ready + 8 * c, kEpiWarps);
-    mbar_init(bar_acc_full, 1);
-    mbar_init(bar_acc_full + 8, 1);
+    mbar_init(bar_acc_full, kMmaWarps);
+    mbar_init(bar_acc_full + 8, kMmaWarps);
+    mbar_init(bar_token, 1);
+    mbar_init(bar_token + 8, 1);
     mbar_init(bar_pos_full, kEncWarps);
     mbar_init(bar_pos_empty, 1);
     mbar_init(bar_dir_full, kEncWarps);
@@ -125,6 +177,12 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
     tmem_alloc(tmem_slot, kTmemCols2);
     tmem_relinquish();
   }
+  // biases: constant bank -> shared memory (the epilogue reads them as broadcast LDS.128;
+  // indexed constant loads miss the small constant cache and serialise the epilogue)
+  for (int i = threadIdx.x; i < prog.n_gemm * 256; i += kThreads2)
+    reinterpret_cast<float*>(smem + S::bias)[i] = c_small2[kSmallBias + i];
+  for (int i = threadIdx.x; i < 640; i += kThreads2)  // sigma_w[256] then rgb_w[3][128]: contiguous in the block
+    reinterpret_cast<float*>(smem + S::heads)[i] = c_small2[kSmallSigmaW + i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -139,8 +197,10 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
         const GemmLayer& L = prog.layer[g];
         const int nchunks = L.n_act_chunks + L.use_aux;
         const uint32_t bytes = (uint32_t)L.n_halves * kBlockBytes;
-        for (int c = 0; c < nchunks; ++c, ++cnt) {
+        for (int i = 0; i < nchunks; ++i, ++cnt) {
           if ((int)(cnt % kProdWarps) != me) continue;
+          // consumption order: the encoding chunk (last block of the layer) first
+          const int c = L.use_aux ? (i == 0 ? L.n_act_chunks : i - 1) : i;
           const uint32_t stage = cnt % kStages, phase = (cnt / kStages) & 1;
           mbar_wait(bar_w_empty + 8 * stage, phase ^ 1);
           if (lane == 0) {
@@ -153,74 +213,81 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
         }
       }
     }
-  } else if (warp == kWarpMma) {
-    // ------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc256 = umma_idesc_bf16(128, 256, 0, 0);
-    constexpr uint32_t idesc128 = umma_idesc_bf16(128, 128, 0, 0);
-    uint32_t cnt = 0, a_cnt = 0, acc_cnt[2] = {0, 0};
+  } else if (warp >= kWarpMma) {
+    // ------------------------------------------------ MMA issuers
+    // A tcgen05.mma blocks at issue until the previous MMA has (nearly) finished, and the
+    // tensor pipe idles whenever no MMA is waiting at that point (tools/mma_bench.cu).  One
+    // warp cannot do the per-chunk bookkeeping (operand waits, descriptor set-up, commits:
+    // 400+ cycles of mostly dependent uniform-datapath instructions) inside the 512 cycles of a
+    // chunk's four MMAs, so TWO warps alternate chunks: while one is blocked issuing the MMAs of
+    // chunk c, the other prepares chunk c+1 and then queues behind it.  A token mbarrier,
+    // passed right after a warp's last MMA issue, keeps the issue order.
+    //  * all 32 lanes run the loop in lock step on provably uniform values (table in kernel
+    //    parameters, TMEM base 0, vote-based waits); tcgen05 instructions are guarded to lane 0
+    //  * within a layer the encoding chunk (smem operand, independent of the previous
+    //    epilogue) goes FIRST and fills the bubble while the epilogue converts chunk 0
+    //  * each accumulator-full barrier expects one commit per issuer (the table says who)
+    if (tmem_base != 0) __trap();  // 512 columns = the whole tensor memory
+    const uint32_t me = warp - kWarpMma;
+    const uint32_t issue = (lane == 0) ? 1u : 0u;
+    const int n_rec = tab.n;
+    const uint32_t a_tile_odd = tab.a_tile_odd;
+    int64_t tile = blockIdx.x;
     uint32_t titer = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
-      for (int g = 0; g < n_gemm; ++g) {
-        const GemmLayer& L = prog.layer[g];
-        const uint32_t d_col = tmem_base + (uint32_t)(g & 1) * 256u;
-        const uint32_t a_col = tmem_base + (uint32_t)((g + 1) & 1) * 256u;
-        const uint32_t idesc = (L.n_halves == 2) ? idesc256 : idesc128;
-        uint32_t accum = 0;
-        if (lane == 0) FS_TRACE2(titer, g, 0);
-        for (int c = 0; c < L.n_act_chunks; ++c, ++cnt) {
-          mbar_wait(bar_a_ready + 8 * c, a_cnt & 1);
-          const uint32_t stage = cnt % kStages, phase = (cnt / kStages) & 1;
-          mbar_wait(bar_w_full + 8 * stage, phase);
-          tc_fence_after();
-          if (lane == 0) {
-            if (c == 0) FS_TRACE2(titer, g, 1);
-            const uint32_t b_tile = sbase + S::ring + stage * kStageBytes;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // chunk c: features [0,32) packed at columns 64c.., [32,64) at 64c+32..
-              umma_bf16_ts(d_col, a_col + 64 * c + 32 * (k >> 1) + 8 * (k & 1),
-                           umma_desc_sw128(b_tile + k * 32, 16, 1024), idesc, accum);
-              accum = 1;
-            }
-            umma_commit(bar_w_empty + 8 * stage);
-          }
-          __syncwarp();
-        }
-        if (L.n_act_chunks) ++a_cnt;
-        if (L.use_aux) {
-          const bool is_dir = (L.epi == EPI_BRANCH);
-          mbar_wait(is_dir ? bar_dir_full : bar_pos_full, titer & 1);
-          const uint32_t stage = cnt % kStages, phase = (cnt / kStages) & 1;
-          mbar_wait(bar_w_full + 8 * stage, phase);
-          tc_fence_after();
-          if (lane == 0) {
-            if (L.n_act_chunks == 0) FS_TRACE2(titer, g, 1);
-            const uint32_t a_tile = sbase + (is_dir ? S::aux_dir : S::aux_pos);
-            const uint32_t b_tile = sbase + S::ring + stage * kStageBytes;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_bf16_ss(d_col, umma_desc_sw128(a_tile + k * 32, 16, 1024),
-                           umma_desc_sw128(b_tile + k * 32, 16, 1024), idesc, accum);
-              accum = 1;
-            }
-            umma_commit(bar_w_empty + 8 * stage);
-            if (is_dir) umma_commit(bar_dir_empty);
-            else if (g == last_pos_user) umma_commit(bar_pos_empty);
-          }
-          __syncwarp();
-          ++cnt;
-        }
-        if (lane == 0) {
-          umma_commit(bar_acc_full + 8 * (g & 1));
-          FS_TRACE2(titer, g, 2);
-        }
-        __syncwarp();
-        ++acc_cnt[g & 1];
+    int j = (int)me;
+    if (j >= n_rec) { j -= n_rec; tile += gridDim.x; ++titer; }
+    uint32_t stage = me % kStages, wpar = 0, tok_par = me ? 0u : 1u, n_mine = 0;
+    while (tile < n_tiles) {
+      const IssueRec& R = tab.rec[j];
+      const uint32_t flags = R.flags, idesc = R.idesc;
+      const bool is_tmem = flags & kRecTmem, first = flags & kRecFirst;
+      const uint32_t d_col = flags & kRecDcol;
+      const uint32_t g_cur = flags >> 24;
+      const uint32_t a0 = is_tmem ? R.a0 : umma_desc_lo(sbase + R.a0);
+      const uint32_t b0 = umma_desc_lo(sbase + S::ring + stage * kStageBytes);
+      const uint32_t apar = (flags & kRecParTile) ? (titer & 1u) : (((titer & a_tile_odd) ^ (flags >> kRecParShift)) & 1u);
+      if (args.trace && lane == 0 && first) FS_TRACE2(titer, g_cur, 0);
+      mbar_wait_converged(bar_w_full + 8 * stage, wpar);
+      mbar_wait_converged(sbase + R.abar, apar);
+      mbar_wait_converged(bar_token + 8 * me, tok_par);  // the other issuer has queued its chunk
+      tok_par ^= 1u;
+      tc_fence_after();
+      if (args.trace && lane == 0 && first) FS_TRACE2(titer, g_cur, 1);
+      if (is_tmem) {  // features [0,32) of the chunk at columns +0, +8; [32,64) at +32, +40
+        umma_bf16_ts_conv(d_col, a0, umma_desc_from_lo(b0), idesc, first ? 0u : 1u, issue);
+        umma_bf16_ts_conv(d_col, a0 + 8, umma_desc_from_lo(b0 + 2), idesc, 1u, issue);
+        umma_bf16_ts_conv(d_col, a0 + 32, umma_desc_from_lo(b0 + 4), idesc, 1u, issue);
+        umma_bf16_ts_conv(d_col, a0 + 40, umma_desc_from_lo(b0 + 6), idesc, 1u, issue);
+      } else {
+        umma_bf16_ss_conv(d_col, umma_desc_from_lo(a0), umma_desc_from_lo(b0), idesc, first ? 0u : 1u, issue);
+        umma_bf16_ss_conv(d_col, umma_desc_from_lo(a0 + 2), umma_desc_from_lo(b0 + 2), idesc, 1u, issue);
+        umma_bf16_ss_conv(d_col, umma_desc_from_lo(a0 + 4), umma_desc_from_lo(b0 + 4), idesc, 1u, issue);
+        umma_bf16_ss_conv(d_col, umma_desc_from_lo(a0 + 6), umma_desc_from_lo(b0 + 6), idesc, 1u, issue);
       }
-      // the next tile's first layer overwrites region 0, which the last layer still
-      // reads as its A operand: let the tensor pipe drain first
-      const int gl = n_gemm - 1;
-      mbar_wait(bar_acc_full + 8 * (gl & 1), (acc_cnt[gl & 1] - 1) & 1);
+      if (lane == 0) mbar_arrive(bar_token + 8 * (me ^ 1u));  // the last MMA is queued: hand over
+      __syncwarp();
+      umma_commit_conv(bar_w_empty + 8 * stage, issue);
+      if (R.xbar) umma_commit_conv(sbase + R.xbar, issue);
+      const uint32_t n_acc = R.n_acc;
+      if (n_acc) {
+        umma_commit_conv(sbase + R.accbar, issue);
+        if (n_acc > 1) umma_commit_conv(sbase + R.accbar, issue);
+        if (args.trace && lane == 0 && R.pad) FS_TRACE2(titer, g_cur, 2);
+      }
+      // next chunk of mine
+      ++n_mine;
+      j += kMmaWarps;
+      stage += kMmaWarps;
+      if (stage >= kStages) { stage -= kStages; wpar ^= 1u; }
+      if (j >= n_rec) {
+        j -= n_rec; tile += gridDim.x;
+        // the next tile's first layer overwrites region 0, which the last layer still reads as
+        // its A operand: let the tensor pipe drain first (completion index of that barrier:
+        // last_acc_n per tile)
+        if (tile < n_tiles)
+          mbar_wait_converged(sbase + tab.last_acc_off, ((titer + 1) * tab.last_acc_n - 1) & 1u);
+        ++titer;
+      }
     }
   } else if (warp >= kWarpEnc0) {
     // ------------------------------------------------ encoders (thread = sample row)
@@ -314,71 +381,76 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
         if (threadIdx.x == 0) FS_TRACE2(titer, g, 4);
         float part[3] = {0.f, 0.f, 0.f};
         float sig_part = 0.f;
-        uint32_t v[2][32];
-        tmem_ld32(region + 32 * half, v[0]);
+        // rolled on purpose: the kernel's hot loops must stay instruction-cache resident
+        // (the MMA issue loop shares the SM's I-cache with this code)
+#pragma unroll 1
+        for (int c = 0; c < nchunk; ++c) {
+          const int c0 = 64 * c + 32 * half;  // first feature handled by this thread
+          uint32_t v[32];
+          tmem_ld32(region + c0, v);
+          float4 b4[8];
+          {
+            const float4* __restrict__ sb = reinterpret_cast<const float4*>(smem + S::bias) + ((g * 256 + c0) >> 2);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c < nchunk) {
-            const int c0 = 64 * c + 32 * half;  // first feature handled by this thread
-            tmem_ld_wait();
-            if (c + 1 < nchunk) tmem_ld32(region + 64 * (c + 1) + 32 * half, v[(c + 1) & 1]);
-            const uint32_t(&vc)[32] = v[c & 1];
-            const float2* __restrict__ cb2 =
-                reinterpret_cast<const float2*>(c_small2 + kSmallBias + g * 256 + c0);
-            uint32_t w[16];
-            if (epi == EPI_RELU || epi == EPI_CONN) {
+            for (int i = 0; i < 8; ++i) b4[i] = sb[i];
+          }
+          tmem_ld_wait();
+          uint32_t w[16];
+          if (epi == EPI_RELU || epi == EPI_CONN) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float2 b = cb2[i];
-                float s0, s1;
-                add_f32x2(s0, s1, __uint_as_float(vc[2 * i]), __uint_as_float(vc[2 * i + 1]), b.x, b.y);
-                w[i] = (epi == EPI_RELU) ? pack_bf16x2_relu(s0, s1) : pack_bf16x2(s0, s1);
-              }
-            } else {
-              float h[32];
+            for (int i = 0; i < 8; ++i) {
+              float s0, s1, s2, s3;
+              add_f32x2(s0, s1, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), b4[i].x, b4[i].y);
+              add_f32x2(s2, s3, __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]), b4[i].z, b4[i].w);
+              w[2 * i] = (epi == EPI_RELU) ? pack_bf16x2_relu(s0, s1) : pack_bf16x2(s0, s1);
+              w[2 * i + 1] = (epi == EPI_RELU) ? pack_bf16x2_relu(s2, s3) : pack_bf16x2(s2, s3);
+            }
+          } else {
+            // last hidden layer (+ sigma head) / branch layer (+ rgb head): heads on CUDA cores
+            const float* hw = reinterpret_cast<const float*>(smem + S::heads) + (epi == EPI_RELU_SIGMA ? 0 : 256) + c0;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float2 b = cb2[i];
-                h[2 * i] = fmaxf(__uint_as_float(vc[2 * i]) + b.x, 0.f);
-                h[2 * i + 1] = fmaxf(__uint_as_float(vc[2 * i + 1]) + b.y, 0.f);
-                w[i] = pack_bf16x2(h[2 * i], h[2 * i + 1]);
-              }
+            for (int i = 0; i < 8; ++i) {
+              const float h0 = fmaxf(__uint_as_float(v[4 * i]) + b4[i].x, 0.f);
+              const float h1 = fmaxf(__uint_as_float(v[4 * i + 1]) + b4[i].y, 0.f);
+              const float h2 = fmaxf(__uint_as_float(v[4 * i + 2]) + b4[i].z, 0.f);
+              const float h3 = fmaxf(__uint_as_float(v[4 * i + 3]) + b4[i].w, 0.f);
+              w[2 * i] = pack_bf16x2(h0, h1);
+              w[2 * i + 1] = pack_bf16x2(h2, h3);
+              const float4 w0 = *reinterpret_cast<const float4*>(hw + 4 * i);
               if (epi == EPI_RELU_SIGMA) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) sig_part = fmaf(h[i], c_small2[kSmallSigmaW + c0 + i], sig_part);
+                sig_part = fmaf(h0, w0.x, fmaf(h1, w0.y, fmaf(h2, w0.z, fmaf(h3, w0.w, sig_part))));
               } else {
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-#pragma unroll
-                  for (int i = 0; i < 32; ++i)
-                    part[ch] = fmaf(h[i], c_small2[kSmallRgbW + ch * 128 + c0 + i], part[ch]);
-                }
+                const float4 w1 = *reinterpret_cast<const float4*>(hw + 128 + 4 * i);
+                const float4 w2 = *reinterpret_cast<const float4*>(hw + 256 + 4 * i);
+                part[0] = fmaf(h0, w0.x, fmaf(h1, w0.y, fmaf(h2, w0.z, fmaf(h3, w0.w, part[0]))));
+                part[1] = fmaf(h0, w1.x, fmaf(h1, w1.y, fmaf(h2, w1.z, fmaf(h3, w1.w, part[1]))));
+                part[2] = fmaf(h0, w2.x, fmaf(h1, w2.y, fmaf(h2, w2.z, fmaf(h3, w2.w, part[2]))));
               }
             }
-            if (!last) {
-              // bf16 pairs back into TMEM over the first 16 of the 32 fp32 columns just read
-              tmem_st16(region + c0, w);
-              tmem_st_wait();
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar_a_ready + 8 * c);
-            }
-            if (kTrain) {
-              // SW128 image slab of this quarter's 32 rows of chunk c -> stash
-              const uint32_t buf = stage_base + (n_staged % kStageBufs) * kSlabBytes2;
+          }
+          if (!last) {
+            // bf16 pairs back into TMEM over the first 16 of the 32 fp32 columns just read
+            tmem_st16(region + c0, w);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a_ready + 8 * c);
+          }
+          if (kTrain) {
+            // SW128 image slab of this quarter's 32 rows of chunk c -> stash
+            const uint32_t buf = stage_base + (n_staged % kStageBufs) * kSlabBytes2;
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                st_shared_v4(buf + lane * 128 + (((uint32_t)(4 * half + j) ^ (uint32_t)(lane & 7)) << 4),
-                             w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-              fence_proxy_async_smem();
-              if (issuer) bulk_wait_read1();  // slabs older than the previous one have been read
-              named_bar_sync(1 + quarter, 64);
-              if (issuer) {
-                bulk_s2g(stash_tile + L.stash_off + c * kChunkBytes + quarter * kSlabBytes2, buf, kSlabBytes2);
-                bulk_commit();
-              }
-              ++n_staged;
+            for (int j = 0; j < 4; ++j)
+              st_shared_v4(buf + lane * 128 + (((uint32_t)(4 * half + j) ^ (uint32_t)(lane & 7)) << 4),
+                           w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+            fence_proxy_async_smem();
+            if (issuer) bulk_wait_read1();  // slabs older than the previous one have been read
+            named_bar_sync(1 + quarter, 64);
+            if (issuer) {
+              bulk_s2g(stash_tile + L.stash_off + c * kChunkBytes + quarter * kSlabBytes2, buf, kSlabBytes2);
+              bulk_commit();
             }
+            ++n_staged;
           }
         }
         if (threadIdx.x == 0) FS_TRACE2(titer, g, 5);
@@ -435,6 +507,55 @@ int mlp_forward_v2(const MlpProgram& P, const void* packed, int64_t n_samples, i
   a.rays_o = rays_o; a.rays_d = rays_d; a.t_starts = t_starts; a.t_ends = t_ends;
   a.x = x; a.dirs = dirs; a.mask_pos = mask_pos; a.mask_dir = mask_dir;
   a.density_only = density_only; a.out = out; a.stash = reinterpret_cast<uint8_t*>(stash);
+  FS_REQUIRE(P.n_gemm <= kMaxLayers2, "mlp_forward: at most %d GEMM layers are supported", kMaxLayers2);
+  static IssueTable T;  // host staging (one host thread per device, see header)
+  {
+    const bool train = stash != nullptr;
+    const int n_gemm = density_only ? P.n_hidden : P.n_gemm;
+    int last_pos_user = 0;
+    for (int g = 0; g < P.n_hidden; ++g)
+      if (P.layer[g].use_aux) last_pos_user = g;
+    auto bar = [&](int off_train, int off_infer) { return (uint32_t)(train ? off_train : off_infer); };
+    int j = 0, cons = 0;
+    for (int g = 0; g < n_gemm; ++g) {
+      const GemmLayer& L = P.layer[g];
+      const int nch = L.n_act_chunks + L.use_aux;
+      const bool is_dir = (L.epi == EPI_BRANCH);
+      FS_REQUIRE(j + nch <= kMaxChunks2, "mlp_forward: more than %d K chunks per tile", kMaxChunks2);
+      for (int i = 0; i < nch; ++i, ++j) {
+        const int c = i - L.use_aux;  // -1: the encoding chunk (first)
+        IssueRec& R = T.rec[j];
+        R.flags = ((uint32_t)g << 24) | ((g & 1) ? kRecDcol : 0u) | (i == 0 ? kRecFirst : 0u);
+        R.xbar = 0;
+        if (c >= 0) {
+          R.flags |= kRecTmem | ((uint32_t)(cons & 1) << kRecParShift);
+          R.a0 = (uint32_t)((g + 1) & 1) * 256u + 64u * c;
+          R.abar = bar(Bars<true>::a_ready, Bars<false>::a_ready) + 8 * c;
+        } else {
+          R.flags |= kRecParTile;
+          R.a0 = is_dir ? bar(Smem<true>::aux_dir, Smem<false>::aux_dir) : bar(Smem<true>::aux_pos, Smem<false>::aux_pos);
+          R.abar = is_dir ? bar(Bars<true>::dir_full, Bars<false>::dir_full)
+                          : bar(Bars<true>::pos_full, Bars<false>::pos_full);
+          if (is_dir) R.xbar = bar(Bars<true>::dir_empty, Bars<false>::dir_empty);
+          else if (g == last_pos_user) R.xbar = bar(Bars<true>::pos_empty, Bars<false>::pos_empty);
+        }
+        R.idesc = (L.n_halves == 2) ? umma_idesc_bf16(128, 256, 0, 0) : umma_idesc_bf16(128, 128, 0, 0);
+        // accumulator-full barrier: one commit per issuer.  Chunks alternate between the two
+        // issuers, so the last chunk's issuer commits once and the previous chunk's issuer once;
+        // a single-chunk layer's issuer commits twice.
+        R.accbar = bar(Bars<true>::acc_full, Bars<false>::acc_full) + 8 * (g & 1);
+        R.n_acc = (i == nch - 1) ? (nch == 1 ? 2u : 1u) : (i == nch - 2 ? 1u : 0u);
+        R.pad = (i == nch - 1) ? 1u : 0u;  // trace: the layer's last chunk
+      }
+      if (L.n_act_chunks) ++cons;
+    }
+    T.n = j;
+    T.a_tile_odd = (uint32_t)(cons & 1);
+    T.last_acc_off = bar(Bars<true>::acc_full, Bars<false>::acc_full) + 8 * ((n_gemm - 1) & 1);
+    T.last_acc_n = 0;
+    for (int g = 0; g < n_gemm; ++g)
+      if ((g & 1) == ((n_gemm - 1) & 1)) ++T.last_acc_n;
+  }
   const int64_t n_tiles = (n_samples + kTileM - 1) / kTileM;
   const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
   cudaError_t e = cudaMemcpyToSymbolAsync(c_small2, a.packed + P.small_off, kSmallFloats * sizeof(float), 0,
@@ -445,9 +566,9 @@ int mlp_forward_v2(const MlpProgram& P, const void* packed, int64_t n_samples, i
   }
   FsProfScope prof_(stash ? "mlp_fwd_train" : "mlp_fwd", stream);
   if (stash)
-    mlp_fwd2_kernel<true><<<grid, kThreads2, Smem<true>::total, (cudaStream_t)stream>>>(P, a);
+    mlp_fwd2_kernel<true><<<grid, kThreads2, Smem<true>::total, (cudaStream_t)stream>>>(P, a, T);
   else
-    mlp_fwd2_kernel<false><<<grid, kThreads2, Smem<false>::total, (cudaStream_t)stream>>>(P, a);
+    mlp_fwd2_kernel<false><<<grid, kThreads2, Smem<false>::total, (cudaStream_t)stream>>>(P, a, T);
   return fsnerf_check_launch("mlp_forward");
 }
 

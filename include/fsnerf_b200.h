@@ -152,7 +152,7 @@ int fsnerf_profile_enable(int on);
 /* Sum the recorded times by kernel name (synchronises the recorded events).
  * names: max_kernels x 32 chars; returns the number of distinct kernels. */
 int fsnerf_profile_read(int max_kernels, char* names, float* total_ms, int* counts);
-/* tuning aid: device buffer of >= 4*16*8 int64 that CTA 0 of the MLP forward fills
+/* tuning aid: device buffer of >= 2048 int64 that CTA 0 of the MLP forward fills
  * with clock64 phase timestamps (NULL disables; tools/trace_fwd.py decodes it). */
 int fsnerf_debug_set_trace(void* buf);
 
