@@ -13,6 +13,7 @@
 //         images used MN-major; persistent CTAs own (layer, tile-range) entries,
 //         accumulate in TMEM and flush once with fp32 atomics.
 //  heads  SIMT column sums for the degenerate (N=1 / N=3) sigma and rgb heads.
+#include <stdlib.h>
 #include "common.cuh"
 #include "mlp_common.cuh"
 
@@ -606,11 +607,20 @@ extern "C" int fsnerf_mlp_backward(const fsnerf_net_cfg* cfg, const float* param
       return FSNERF_ERR_CUDA;
     }
   }
-  {
-    FsProfScope prof_("mlp_dgrad", stream);
-    mlp_dgrad_kernel<<<grid, kThreads, kSmemTotal, st>>>(P, BP, ba);
+  static int variant = -1;  // FSNERF_BWD_VARIANT: unset / 2 = tensor-memory dgrad (mlp_bwd2.cu), 1 = first generation
+  if (variant < 0) {
+    const char* e = getenv("FSNERF_BWD_VARIANT");
+    variant = e ? atoi(e) : 2;
   }
-  rc = fsnerf_check_launch("mlp_backward(dgrad)");
+  if (variant == 2) {
+    rc = mlp_dgrad_v2(P, packed, n_samples, stash, out, d_out, grads, workspace, stream);
+  } else {
+    {
+      FsProfScope prof_("mlp_dgrad", stream);
+      mlp_dgrad_kernel<<<grid, kThreads, kSmemTotal, st>>>(P, BP, ba);
+    }
+    rc = fsnerf_check_launch("mlp_backward(dgrad)");
+  }
   if (rc != FSNERF_OK) return rc;
   // ---- heads
   HeadsArgs ha;

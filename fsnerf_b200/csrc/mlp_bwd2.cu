@@ -1,0 +1,387 @@
+// Kernel (3) backward, second generation dgrad: the fused d(pre-activation) chain of the
+// NeRF MLP with the gradients resident in TENSOR MEMORY (the loss.backward() edge of
+// src/run-nerf.py:282 through src/core/models.py:111-143).  Same skeleton as mlp_fwd2.cu:
+//   warps 0..7   epilogue: TMEM -> regs -> (+ sigma-head term) -> ReLU mask from the forward
+//                stash -> bf16x2 written back IN PLACE as the next step's A operand; every
+//                finished chunk is handed to the MMA warps, staged through smem per 32-row
+//                slab and bulk-stored to the dstash image that wgrad streams back.
+//   warps 8..11  reducers: column sums of each staged slab = bias gradients (smem atomics)
+//   warps 12,13  MMA issuers, alternating chunks (mlp_issue.cuh): D[128 x 256] = dpre . W
+//                with W^T operand stages; the two TMEM regions alternate roles per step
+//   warps 14,15  weight producers
+// The seed step (d(out) -> rgb head^T -> branch-layer dpre) runs on CUDA cores in the
+// epilogue warps.
+#include "common.cuh"
+#include "mlp_common.cuh"
+#include "mlp_issue.cuh"
+
+namespace fs {
+namespace {
+
+constexpr int kEpiWarpsB = 8;
+constexpr int kRedWarpsB = 4;
+constexpr int kWarpRed0 = kEpiWarpsB;                 // 8
+constexpr int kWarpMmaB = kEpiWarpsB + kRedWarpsB;    // 12, 13
+constexpr int kWarpProdB = kWarpMmaB + kMmaWarps;     // 14, 15
+constexpr int kThreadsB = (kWarpProdB + kProdWarps) * 32;  // 512
+constexpr int kStagesB = 4;
+constexpr int kSlabBytesB = 32 * 128;
+constexpr int kStageBufsB = 3;
+constexpr int kMaxLayersB = 12;
+
+struct SmemB {
+  static constexpr int ring = 0;
+  static constexpr int staging = ring + kStagesB * kStageBytes;
+  static constexpr int bias = staging + 4 * kStageBufsB * kSlabBytesB;   // fp32 [kMaxLayersB][256]
+  static constexpr int heads = bias + kMaxLayersB * 256 * 4;             // sigma_w[256], rgb_w[3][128]
+  static constexpr int bars = heads + 640 * 4;
+  static constexpr int total = bars + 256;
+};
+struct BarsB {
+  static constexpr int w_full = SmemB::bars;
+  static constexpr int w_empty = w_full + 8 * kStagesB;
+  static constexpr int a_ready = w_empty + 8 * kStagesB;  // [4]
+  static constexpr int acc_full = a_ready + 8 * 4;        // [2]
+  static constexpr int token = acc_full + 8 * 2;          // [2]
+  static constexpr int tmem_slot = token + 16;
+};
+
+__constant__ float c_smallB[kSmallFloats];
+
+struct StepB {
+  int target;      // layer whose d(pre-activation) this step produces
+  int mask_off;    // stash offset of the target's forward output (ReLU mask), -1: none
+  int add_sigma;   // add d(sigma) * w_sigma (target is the last hidden layer)
+  int dstash_off;  // where the target's dpre image goes in the backward record
+};
+struct PlanB {
+  int n_steps;
+  int g_branch, branch_mask_off, branch_dstash_off;
+  StepB step[kMaxGemm];
+};
+struct ArgsB {
+  long long* trace;
+  const uint8_t* packed;
+  int64_t n_samples;
+  const uint8_t* stash;
+  const float* out;
+  const float* d_out;
+  float* grads;
+  uint8_t* dstash;
+};
+
+__device__ __forceinline__ uint4 ldg_u4(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+__global__ void __launch_bounds__(kThreadsB, 1)
+mlp_dgrad2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ PlanB plan,
+                  const __grid_constant__ ArgsB args, const __grid_constant__ IssueTable tab) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_w_full = sbase + BarsB::w_full;
+  const uint32_t bar_w_empty = sbase + BarsB::w_empty;
+  const uint32_t bar_a_ready = sbase + BarsB::a_ready;
+  const uint32_t bar_acc_full = sbase + BarsB::acc_full;
+  const uint32_t bar_token = sbase + BarsB::token;
+  const uint32_t tmem_slot = sbase + BarsB::tmem_slot;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + BarsB::tmem_slot);
+  float* bias_acc = reinterpret_cast<float*>(smem + SmemB::bias);
+  const float* heads = reinterpret_cast<const float*>(smem + SmemB::heads);
+  const int64_t n_tiles = (args.n_samples + kTileM - 1) / kTileM;
+
+  if ((sbase & 1023u) != 0) __trap();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStagesB; ++s) {
+      mbar_init(bar_w_full + 8 * s, 1);
+      mbar_init(bar_w_empty + 8 * s, 1);
+    }
+    for (int c = 0; c < 4; ++c) mbar_init(bar_a_ready + 8 * c, kEpiWarpsB);
+    mbar_init(bar_acc_full, kMmaWarps);
+    mbar_init(bar_acc_full + 8, kMmaWarps);
+    mbar_init(bar_token, 1);
+    mbar_init(bar_token + 8, 1);
+    fence_barrier_init();
+  }
+  if (warp == kWarpMmaB) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < kMaxLayersB * 256; i += kThreadsB) bias_acc[i] = 0.f;
+  for (int i = threadIdx.x; i < 640; i += kThreadsB)
+    reinterpret_cast<float*>(smem + SmemB::heads)[i] = c_smallB[kSmallSigmaW + i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp >= kWarpProdB) {
+    IssueBars IB{bar_w_full, bar_w_empty, bar_token, sbase + SmemB::ring};
+    producer_loop<kStagesB>(tab, IB, args.packed, n_tiles, warp - kWarpProdB, lane);
+  } else if (warp >= kWarpMmaB) {
+    if (tmem_base != 0) __trap();
+    IssueBars IB{bar_w_full, bar_w_empty, bar_token, sbase + SmemB::ring};
+    issuer_loop<kStagesB>(tab, IB, sbase, n_tiles, (uint32_t)(warp - kWarpMmaB), lane, args.trace);
+  } else if (warp >= kWarpRed0) {
+    // ------------------------------------------------ reducers: bias gradients
+    // one warp per lane quarter; after the quarter's slab barrier it sums the slab's 32 rows:
+    // lane l owns features 2l, 2l+1 of the 64-feature chunk (conflict-free 4 B reads)
+    const int quarter = warp - kWarpRed0;
+    const uint32_t stage_base = sbase + SmemB::staging + quarter * (kStageBufsB * kSlabBytesB);
+    uint32_t n_staged = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int s = -1; s < plan.n_steps; ++s) {
+        const int layer = (s < 0) ? plan.g_branch : plan.step[s].target;
+        const int nchunk = (s < 0) ? 2 : 4;
+        for (int c = 0; c < nchunk; ++c, ++n_staged) {
+          const uint32_t buf = stage_base + (n_staged % kStageBufsB) * kSlabBytesB;
+          named_bar_sync(1 + quarter, 96);
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            uint32_t w;
+            asm volatile("ld.shared.b32 %0, [%1];"
+                         : "=r"(w)
+                         : "r"(buf + r * 128 + ((((uint32_t)lane >> 2) ^ (uint32_t)(r & 7)) << 4) + ((lane & 3) << 2)));
+            s0 += bf16_lo(w);
+            s1 += bf16_hi(w);
+          }
+          atomicAdd(bias_acc + layer * 256 + 64 * c + 2 * lane, s0);
+          atomicAdd(bias_acc + layer * 256 + 64 * c + 2 * lane + 1, s1);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t stage_base = sbase + SmemB::staging + quarter * (kStageBufsB * kSlabBytesB);
+    const bool issuer = half == 0 && lane == 0;
+    uint32_t acc_phase[2] = {0, 0};
+    uint32_t n_staged = 0;
+    uint32_t titer = 0;
+    // stage the 32 bf16 of this thread (16 words) into the quarter's slab, hand it to the
+    // reducer and to the bulk store (SW128 image: unit u of row r at r*128 + ((u ^ (r&7)) << 4))
+    auto stage_out = [&](const uint32_t (&w)[16], uint8_t* dst) {
+      const uint32_t buf = stage_base + (n_staged % kStageBufsB) * kSlabBytesB;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        st_shared_v4(buf + lane * 128 + (((uint32_t)(4 * half + j) ^ (uint32_t)(lane & 7)) << 4), w[4 * j],
+                     w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+      fence_proxy_async_smem();
+      if (issuer) bulk_wait_read1();  // slabs older than the previous one have been read
+      named_bar_sync(1 + quarter, 96);
+      if (issuer) {
+        bulk_s2g(dst, buf, kSlabBytesB);
+        bulk_commit();
+      }
+      ++n_staged;
+    };
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
+      const int64_t p = tile * kTileM + row;
+      const bool valid = p < args.n_samples;
+      const uint8_t* stash_tile = args.stash + (size_t)tile * prog.stash_tile_bytes;
+      uint8_t* dstash_tile = args.dstash + (size_t)tile * prog.dstash_tile_bytes;
+      // ---- seed: d(out) -> rgb head^T -> d(pre-activation) of the branch layer (128 wide)
+      float dz[3] = {0.f, 0.f, 0.f}, dsig = 0.f;
+      if (valid) {
+        const float4 o4 = __ldg(reinterpret_cast<const float4*>(args.out) + p);
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(args.d_out) + p);
+        dz[0] = g4.x * o4.x * (1.0f - o4.x);  // sigmoid'
+        dz[1] = g4.y * o4.y * (1.0f - o4.y);
+        dz[2] = g4.z * o4.z * (1.0f - o4.z);
+        dsig = g4.w;
+      }
+      const uint32_t my_units = (uint32_t)(4 * half);
+      uint4 m[4];
+      {
+        const uint8_t* hb = stash_tile + plan.branch_mask_off;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          const int c0 = 64 * c + 32 * half;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) m[j] = ldg_u4(hb + c * kChunkBytes + sw128_off(row, my_units + j));
+          if (half == 0 && plan.n_steps > 0 && plan.step[0].mask_off >= 0)
+            prefetch_l2(stash_tile + plan.step[0].mask_off + c * kChunkBytes + row * 128);
+          uint32_t w[16];
+          const float* wr = heads + 256 + c0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t mw[4] = {m[j].x, m[j].y, m[j].z, m[j].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int i = 8 * j + 2 * q;
+              float v0 = dz[0] * wr[i] + dz[1] * wr[128 + i] + dz[2] * wr[256 + i];
+              float v1 = dz[0] * wr[i + 1] + dz[1] * wr[128 + i + 1] + dz[2] * wr[256 + i + 1];
+              if ((mw[q] & 0x00007FFFu) == 0u) v0 = 0.f;  // relu'(h): h == 0 <=> masked
+              if ((mw[q] & 0x7FFF0000u) == 0u) v1 = 0.f;
+              w[4 * j + q] = pack_bf16x2(v0, v1);
+            }
+          }
+          // step 0 reads its A operand from region 1
+          tmem_st16(tmem_lane + 256u + c0, w);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_a_ready + 8 * c);
+          stage_out(w, dstash_tile + plan.branch_dstash_off + c * kChunkBytes + quarter * kSlabBytesB);
+        }
+      }
+      // ---- chain
+      for (int s = 0; s < plan.n_steps; ++s) {
+        const StepB S = plan.step[s];
+        const int r = s & 1;
+        const uint32_t region = tmem_lane + (uint32_t)r * 256u;
+        const bool last = (s == plan.n_steps - 1);
+        const uint8_t* mimg = (S.mask_off >= 0) ? stash_tile + S.mask_off : nullptr;
+        const uint8_t* mnext = (!last && plan.step[s + 1].mask_off >= 0) ? stash_tile + plan.step[s + 1].mask_off : nullptr;
+        const bool add_sigma = S.add_sigma != 0;
+        // chunk 0's mask does not depend on the MMAs: fetch it before waiting on the accumulator
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          m[j] = mimg ? ldg_u4(mimg + sw128_off(row, my_units + j)) : make_uint4(~0u, ~0u, ~0u, ~0u);
+        if (threadIdx.x == 0 && args.trace && blockIdx.x == 0 && titer < 4) args.trace[(titer * 16 + s) * 8 + 3] = clock64();
+        mbar_wait(bar_acc_full + 8 * r, acc_phase[r]);
+        acc_phase[r] ^= 1;
+        tc_fence_after();
+        if (threadIdx.x == 0 && args.trace && blockIdx.x == 0 && titer < 4) args.trace[(titer * 16 + s) * 8 + 4] = clock64();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int c0 = 64 * c + 32 * half;
+          uint32_t v[32];
+          tmem_ld32(region + c0, v);
+          // next chunk's mask (one chunk ahead), next step's mask lines into L2
+          uint4 mn[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            mn[j] = (mimg && c < 3) ? ldg_u4(mimg + (c + 1) * kChunkBytes + sw128_off(row, my_units + j))
+                                    : make_uint4(~0u, ~0u, ~0u, ~0u);
+          if (half == 0 && mnext) prefetch_l2(mnext + c * kChunkBytes + row * 128);
+          tmem_ld_wait();
+          uint32_t w[16];
+          const float* ws = heads + c0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t mw[4] = {m[j].x, m[j].y, m[j].z, m[j].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int i = 8 * j + 2 * q;
+              float v0 = __uint_as_float(v[i]), v1 = __uint_as_float(v[i + 1]);
+              if (add_sigma) {
+                v0 = fmaf(dsig, ws[i], v0);
+                v1 = fmaf(dsig, ws[i + 1], v1);
+              }
+              if ((mw[q] & 0x00007FFFu) == 0u) v0 = 0.f;
+              if ((mw[q] & 0x7FFF0000u) == 0u) v1 = 0.f;
+              w[4 * j + q] = pack_bf16x2(v0, v1);
+            }
+          }
+          if (!last) {
+            tmem_st16(region + c0, w);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a_ready + 8 * c);
+          }
+          stage_out(w, dstash_tile + S.dstash_off + c * kChunkBytes + quarter * kSlabBytesB);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) m[j] = mn[j];
+        }
+        if (threadIdx.x == 0 && args.trace && blockIdx.x == 0 && titer < 4) args.trace[(titer * 16 + s) * 8 + 5] = clock64();
+      }
+    }
+    if (issuer) bulk_wait0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWarpMmaB) tmem_dealloc(tmem_base, 512);
+  // bias gradients of this CTA -> global
+  for (int g = 0; g < prog.n_gemm; ++g) {
+    const int ncols = prog.layer[g].n_halves * 128;
+    if ((int)threadIdx.x < ncols)
+      atomicAdd(args.grads + prog.layer[g].bias_off + threadIdx.x, bias_acc[g * 256 + threadIdx.x]);
+  }
+}
+
+}  // namespace
+
+int mlp_dgrad_v2(const MlpProgram& P, const void* packed, int64_t n_samples, const void* stash, const float* out,
+                 const float* d_out, float* grads, void* workspace, void* stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_dgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemB::total);
+    if (e != cudaSuccess) {
+      fsnerf_set_error("mlp_backward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return FSNERF_ERR_CUDA;
+    }
+    configured = true;
+  }
+  FS_REQUIRE(P.n_gemm <= kMaxLayersB, "mlp_backward: at most %d GEMM layers are supported", kMaxLayersB);
+  static PlanB PL;
+  static IssueTable T;
+  PL.n_steps = P.n_gemm - 1;
+  PL.g_branch = P.n_gemm - 1;
+  PL.branch_mask_off = P.layer[P.n_gemm - 1].stash_off;
+  PL.branch_dstash_off = P.layer[P.n_gemm - 1].dstash_off;
+  int j = 0;
+  int n_cons[4] = {0, 0, 0, 0};
+  for (int s = 0; s < PL.n_steps; ++s)
+    for (int c = 0; c < P.layer[P.n_gemm - 1 - s].bwd_n_chunks; ++c) ++n_cons[c];
+  int cons[4] = {0, 0, 0, 0};
+  for (int s = 0; s < PL.n_steps; ++s) {
+    const int src = P.n_gemm - 1 - s, tgt = src - 1;
+    StepB& S = PL.step[s];
+    S.target = tgt;
+    S.mask_off = (P.layer[tgt].epi == EPI_CONN) ? -1 : P.layer[tgt].stash_off;
+    S.add_sigma = (P.layer[tgt].epi == EPI_RELU_SIGMA) ? 1 : 0;
+    S.dstash_off = P.layer[tgt].dstash_off;
+    const int nch = P.layer[src].bwd_n_chunks;
+    FS_REQUIRE(P.layer[src].bwd_n_halves == 2 && nch <= 4 && j + nch <= kMaxChunks2,
+               "mlp_backward: unsupported layer shape for the tensor-memory dgrad");
+    for (int c = 0; c < nch; ++c, ++j) {
+      IssueRec& R = T.rec[j];
+      // a_ready[c] completes once per producer of chunk c (seed or a step's epilogue) and is
+      // consumed once per step with more than c chunks: index = tile_iter * n_cons[c] + cons[c]
+      R.flags = ((uint32_t)s << 24) | ((s & 1) ? kRecDcol : 0u) | (c == 0 ? kRecFirst : 0u) |
+                (c == nch - 1 ? kRecLast : 0u) | kRecTmem | ((uint32_t)(cons[c] & 1) << kRecParShift) |
+                ((n_cons[c] & 1) ? kRecParTile : 0u);
+      R.idesc = umma_idesc_bf16(128, 256, 0, 0);
+      R.a0 = (uint32_t)((s + 1) & 1) * 256u + 64u * c;
+      R.abar = BarsB::a_ready + 8 * c;
+      R.xbar = 0;
+      R.accbar = BarsB::acc_full + 8 * (s & 1);
+      R.n_acc = issue_n_acc(c, nch);
+      R.w_block = (uint32_t)(P.layer[src].bwd_first_block + c * 2);
+      R.w_bytes = kStageBytes;
+      ++cons[c];
+    }
+  }
+  T.n = j;
+  T.last_acc_off = BarsB::acc_full + 8 * ((PL.n_steps - 1) & 1);
+  T.last_acc_n = 0;
+  for (int s = 0; s < PL.n_steps; ++s)
+    if ((s & 1) == ((PL.n_steps - 1) & 1)) ++T.last_acc_n;
+  ArgsB a;
+  a.trace = reinterpret_cast<long long*>(fsnerf_debug_trace_ptr());
+  a.packed = reinterpret_cast<const uint8_t*>(packed);
+  a.n_samples = n_samples;
+  a.stash = reinterpret_cast<const uint8_t*>(stash);
+  a.out = out; a.d_out = d_out; a.grads = grads;
+  a.dstash = reinterpret_cast<uint8_t*>(workspace);
+  const int64_t n_tiles = (n_samples + kTileM - 1) / kTileM;
+  const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_smallB, a.packed + P.small_off, kSmallFloats * sizeof(float), 0,
+                                          cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    fsnerf_set_error("mlp_backward: constant upload: %s", cudaGetErrorString(e));
+    return FSNERF_ERR_CUDA;
+  }
+  FsProfScope prof_("mlp_dgrad", stream);
+  mlp_dgrad2_kernel<<<grid, kThreadsB, SmemB::total, (cudaStream_t)stream>>>(P, PL, a, T);
+  return fsnerf_check_launch("mlp_backward(dgrad)");
+}
+
+}  // namespace fs

@@ -23,31 +23,21 @@
 #include "common.cuh"
 #include "mlp_common.cuh"
 #include "mlp_encode.cuh"
+#include "mlp_issue.cuh"
 
 namespace fs {
 namespace {
 
 constexpr int kEpiWarps = 8;
 constexpr int kEncWarps = 4;
-constexpr int kProdWarps = 2;
 constexpr int kWarpEnc0 = kEpiWarps;               // 8
-constexpr int kMmaWarps = 2;                       // MMA issuers, alternating K chunks
 constexpr int kWarpMma = kEpiWarps + kEncWarps;    // 12, 13
 constexpr int kWarpProd0 = kWarpMma + kMmaWarps;   // 14
 constexpr int kThreads2 = (kWarpProd0 + kProdWarps) * 32;  // 512
-constexpr int kStageBytes = 2 * kBlockBytes;       // [256 x 64] bf16
 constexpr int kSlabBytes2 = 32 * 128;              // 32 rows of one chunk image
 constexpr int kStageBufs = 3;                      // staging buffers per lane quarter
 constexpr int kTmemCols2 = 512;
 constexpr int kMaxLayers2 = 12;                    // GEMM layers whose biases fit the smem table
-constexpr int kMaxChunks2 = 64;                    // K chunks per tile in the MMA issue table
-// MMA issue table record flags
-constexpr uint32_t kRecDcol = 0x100u;              // accumulator region: TMEM column offset 0 / 256
-constexpr uint32_t kRecTmem = 1u << 16;            // A operand from tensor memory (else smem encoding tile)
-constexpr uint32_t kRecFirst = 1u << 17;           // first chunk of its layer: overwrite the accumulator
-constexpr uint32_t kRecParTile = 1u << 18;         // operand barrier completes once per tile
-constexpr uint32_t kRecParShift = 19;              // bit 19: parity of the consumer-layer index in the tile
-
 template <bool kTrain> __host__ __device__ constexpr int n_stages() { return kTrain ? 4 : 5; }
 template <bool kTrain> struct Smem {
   static constexpr int ring = 0;
@@ -83,28 +73,6 @@ __constant__ float c_small2[kSmallFloats];
     if (args.trace && blockIdx.x == 0 && (slot) < 4)                                        \
       args.trace[((slot) * 16 + (g_)) * 8 + (k_)] = clock64();                              \
   } while (0)
-
-// MMA issue table: one record per 64-wide K chunk of a tile, in consumption order (the
-// encoding chunk of a layer first).  Passed as a __grid_constant__ kernel parameter so the
-// issuing warp reads it with uniform loads: everything it feeds to tcgen05.mma stays in
-// uniform registers (a record fetched from shared memory costs an R2UR waterfall per MMA).
-struct IssueRec {
-  uint32_t flags;    // kRec* | layer << 24
-  uint32_t idesc;
-  uint32_t a0;       // TMEM column of the chunk's A operand, or byte offset of the smem encoding tile
-  uint32_t abar;     // smem byte offset of the operand-ready barrier
-  uint32_t xbar;     // smem byte offset of the "encoding tile free" barrier to commit (0: none)
-  uint32_t accbar;   // smem byte offset of the accumulator-full barrier to commit after the chunk (0: none)
-  uint32_t n_acc;    // how many times to commit it (the barrier expects 2 arrivals per layer, one per issuer)
-  uint32_t pad;
-};
-struct IssueTable {
-  int n;
-  uint32_t a_tile_odd;    // 1 if the number of TMEM-fed layers per tile is odd
-  uint32_t last_acc_off;  // accumulator-full barrier of the tile's last layer (smem byte offset)
-  uint32_t last_acc_n;    // layers per tile sharing that barrier
-  IssueRec rec[kMaxChunks2];
-};
 
 struct Fwd2Args {
   long long* trace;
@@ -190,105 +158,15 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
 
   if (warp >= kWarpProd0) {
     // ------------------------------------------------ weight producers
-    const int me = warp - kWarpProd0;
-    uint32_t cnt = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      for (int g = 0; g < n_gemm; ++g) {
-        const GemmLayer& L = prog.layer[g];
-        const int nchunks = L.n_act_chunks + L.use_aux;
-        const uint32_t bytes = (uint32_t)L.n_halves * kBlockBytes;
-        for (int i = 0; i < nchunks; ++i, ++cnt) {
-          if ((int)(cnt % kProdWarps) != me) continue;
-          // consumption order: the encoding chunk (last block of the layer) first
-          const int c = L.use_aux ? (i == 0 ? L.n_act_chunks : i - 1) : i;
-          const uint32_t stage = cnt % kStages, phase = (cnt / kStages) & 1;
-          mbar_wait(bar_w_empty + 8 * stage, phase ^ 1);
-          if (lane == 0) {
-            mbar_arrive_expect_tx(bar_w_full + 8 * stage, bytes);
-            bulk_g2s(sbase + S::ring + stage * kStageBytes,
-                     args.packed + (size_t)(L.first_block + c * L.n_halves) * kBlockBytes, bytes,
-                     bar_w_full + 8 * stage);
-          }
-          __syncwarp();
-        }
-      }
-    }
+    IssueBars IB{bar_w_full, bar_w_empty, bar_token, sbase + S::ring};
+    producer_loop<kStages>(tab, IB, args.packed, n_tiles, warp - kWarpProd0, lane);
   } else if (warp >= kWarpMma) {
-    // ------------------------------------------------ MMA issuers
-    // A tcgen05.mma blocks at issue until the previous MMA has (nearly) finished, and the
-    // tensor pipe idles whenever no MMA is waiting at that point (tools/mma_bench.cu).  One
-    // warp cannot do the per-chunk bookkeeping (operand waits, descriptor set-up, commits:
-    // 400+ cycles of mostly dependent uniform-datapath instructions) inside the 512 cycles of a
-    // chunk's four MMAs, so TWO warps alternate chunks: while one is blocked issuing the MMAs of
-    // chunk c, the other prepares chunk c+1 and then queues behind it.  A token mbarrier,
-    // passed right after a warp's last MMA issue, keeps the issue order.
-    //  * all 32 lanes run the loop in lock step on provably uniform values (table in kernel
-    //    parameters, TMEM base 0, vote-based waits); tcgen05 instructions are guarded to lane 0
-    //  * within a layer the encoding chunk (smem operand, independent of the previous
-    //    epilogue) goes FIRST and fills the bubble while the epilogue converts chunk 0
-    //  * each accumulator-full barrier expects one commit per issuer (the table says who)
+    // ------------------------------------------------ MMA issuers (mlp_issue.cuh)
+    // Within a layer the encoding chunk (smem operand, independent of the previous epilogue)
+    // goes FIRST in the table: it fills the bubble while the epilogue converts chunk 0.
     if (tmem_base != 0) __trap();  // 512 columns = the whole tensor memory
-    const uint32_t me = warp - kWarpMma;
-    const uint32_t issue = (lane == 0) ? 1u : 0u;
-    const int n_rec = tab.n;
-    const uint32_t a_tile_odd = tab.a_tile_odd;
-    int64_t tile = blockIdx.x;
-    uint32_t titer = 0;
-    int j = (int)me;
-    if (j >= n_rec) { j -= n_rec; tile += gridDim.x; ++titer; }
-    uint32_t stage = me % kStages, wpar = 0, tok_par = me ? 0u : 1u, n_mine = 0;
-    while (tile < n_tiles) {
-      const IssueRec& R = tab.rec[j];
-      const uint32_t flags = R.flags, idesc = R.idesc;
-      const bool is_tmem = flags & kRecTmem, first = flags & kRecFirst;
-      const uint32_t d_col = flags & kRecDcol;
-      const uint32_t g_cur = flags >> 24;
-      const uint32_t a0 = is_tmem ? R.a0 : umma_desc_lo(sbase + R.a0);
-      const uint32_t b0 = umma_desc_lo(sbase + S::ring + stage * kStageBytes);
-      const uint32_t apar = (flags & kRecParTile) ? (titer & 1u) : (((titer & a_tile_odd) ^ (flags >> kRecParShift)) & 1u);
-      if (args.trace && lane == 0 && first) FS_TRACE2(titer, g_cur, 0);
-      mbar_wait_converged(bar_w_full + 8 * stage, wpar);
-      mbar_wait_converged(sbase + R.abar, apar);
-      mbar_wait_converged(bar_token + 8 * me, tok_par);  // the other issuer has queued its chunk
-      tok_par ^= 1u;
-      tc_fence_after();
-      if (args.trace && lane == 0 && first) FS_TRACE2(titer, g_cur, 1);
-      if (is_tmem) {  // features [0,32) of the chunk at columns +0, +8; [32,64) at +32, +40
-        umma_bf16_ts_conv(d_col, a0, umma_desc_from_lo(b0), idesc, first ? 0u : 1u, issue);
-        umma_bf16_ts_conv(d_col, a0 + 8, umma_desc_from_lo(b0 + 2), idesc, 1u, issue);
-        umma_bf16_ts_conv(d_col, a0 + 32, umma_desc_from_lo(b0 + 4), idesc, 1u, issue);
-        umma_bf16_ts_conv(d_col, a0 + 40, umma_desc_from_lo(b0 + 6), idesc, 1u, issue);
-      } else {
-        umma_bf16_ss_conv(d_col, umma_desc_from_lo(a0), umma_desc_from_lo(b0), idesc, first ? 0u : 1u, issue);
-        umma_bf16_ss_conv(d_col, umma_desc_from_lo(a0 + 2), umma_desc_from_lo(b0 + 2), idesc, 1u, issue);
-        umma_bf16_ss_conv(d_col, umma_desc_from_lo(a0 + 4), umma_desc_from_lo(b0 + 4), idesc, 1u, issue);
-        umma_bf16_ss_conv(d_col, umma_desc_from_lo(a0 + 6), umma_desc_from_lo(b0 + 6), idesc, 1u, issue);
-      }
-      if (lane == 0) mbar_arrive(bar_token + 8 * (me ^ 1u));  // the last MMA is queued: hand over
-      __syncwarp();
-      umma_commit_conv(bar_w_empty + 8 * stage, issue);
-      if (R.xbar) umma_commit_conv(sbase + R.xbar, issue);
-      const uint32_t n_acc = R.n_acc;
-      if (n_acc) {
-        umma_commit_conv(sbase + R.accbar, issue);
-        if (n_acc > 1) umma_commit_conv(sbase + R.accbar, issue);
-        if (args.trace && lane == 0 && R.pad) FS_TRACE2(titer, g_cur, 2);
-      }
-      // next chunk of mine
-      ++n_mine;
-      j += kMmaWarps;
-      stage += kMmaWarps;
-      if (stage >= kStages) { stage -= kStages; wpar ^= 1u; }
-      if (j >= n_rec) {
-        j -= n_rec; tile += gridDim.x;
-        // the next tile's first layer overwrites region 0, which the last layer still reads as
-        // its A operand: let the tensor pipe drain first (completion index of that barrier:
-        // last_acc_n per tile)
-        if (tile < n_tiles)
-          mbar_wait_converged(sbase + tab.last_acc_off, ((titer + 1) * tab.last_acc_n - 1) & 1u);
-        ++titer;
-      }
-    }
+    IssueBars IB{bar_w_full, bar_w_empty, bar_token, sbase + S::ring};
+    issuer_loop<kStages>(tab, IB, sbase, n_tiles, (uint32_t)(warp - kWarpMma), lane, args.trace);
   } else if (warp >= kWarpEnc0) {
     // ------------------------------------------------ encoders (thread = sample row)
     const int row = (warp - kWarpEnc0) * 32 + lane;
@@ -512,9 +390,11 @@ int mlp_forward_v2(const MlpProgram& P, const void* packed, int64_t n_samples, i
   {
     const bool train = stash != nullptr;
     const int n_gemm = density_only ? P.n_hidden : P.n_gemm;
-    int last_pos_user = 0;
+    int last_pos_user = 0, n_cons = 0;
     for (int g = 0; g < P.n_hidden; ++g)
       if (P.layer[g].use_aux) last_pos_user = g;
+    for (int g = 0; g < n_gemm; ++g)
+      if (P.layer[g].n_act_chunks) ++n_cons;
     auto bar = [&](int off_train, int off_infer) { return (uint32_t)(train ? off_train : off_infer); };
     int j = 0, cons = 0;
     for (int g = 0; g < n_gemm; ++g) {
@@ -523,16 +403,18 @@ int mlp_forward_v2(const MlpProgram& P, const void* packed, int64_t n_samples, i
       const bool is_dir = (L.epi == EPI_BRANCH);
       FS_REQUIRE(j + nch <= kMaxChunks2, "mlp_forward: more than %d K chunks per tile", kMaxChunks2);
       for (int i = 0; i < nch; ++i, ++j) {
-        const int c = i - L.use_aux;  // -1: the encoding chunk (first)
+        const int c = i - L.use_aux;  // -1: the encoding chunk (first; it is the layer's LAST block)
         IssueRec& R = T.rec[j];
-        R.flags = ((uint32_t)g << 24) | ((g & 1) ? kRecDcol : 0u) | (i == 0 ? kRecFirst : 0u);
+        R.flags = ((uint32_t)g << 24) | ((g & 1) ? kRecDcol : 0u) | (i == 0 ? kRecFirst : 0u) |
+                  (i == nch - 1 ? kRecLast : 0u);
         R.xbar = 0;
         if (c >= 0) {
-          R.flags |= kRecTmem | ((uint32_t)(cons & 1) << kRecParShift);
+          // a_ready[c] completes once per TMEM-fed layer: index = tile_iter * n_cons + cons
+          R.flags |= kRecTmem | ((uint32_t)(cons & 1) << kRecParShift) | ((n_cons & 1) ? kRecParTile : 0u);
           R.a0 = (uint32_t)((g + 1) & 1) * 256u + 64u * c;
           R.abar = bar(Bars<true>::a_ready, Bars<false>::a_ready) + 8 * c;
         } else {
-          R.flags |= kRecParTile;
+          R.flags |= kRecParTile;  // encoding tiles: once per tile
           R.a0 = is_dir ? bar(Smem<true>::aux_dir, Smem<false>::aux_dir) : bar(Smem<true>::aux_pos, Smem<false>::aux_pos);
           R.abar = is_dir ? bar(Bars<true>::dir_full, Bars<false>::dir_full)
                           : bar(Bars<true>::pos_full, Bars<false>::pos_full);
@@ -540,17 +422,14 @@ int mlp_forward_v2(const MlpProgram& P, const void* packed, int64_t n_samples, i
           else if (g == last_pos_user) R.xbar = bar(Bars<true>::pos_empty, Bars<false>::pos_empty);
         }
         R.idesc = (L.n_halves == 2) ? umma_idesc_bf16(128, 256, 0, 0) : umma_idesc_bf16(128, 128, 0, 0);
-        // accumulator-full barrier: one commit per issuer.  Chunks alternate between the two
-        // issuers, so the last chunk's issuer commits once and the previous chunk's issuer once;
-        // a single-chunk layer's issuer commits twice.
         R.accbar = bar(Bars<true>::acc_full, Bars<false>::acc_full) + 8 * (g & 1);
-        R.n_acc = (i == nch - 1) ? (nch == 1 ? 2u : 1u) : (i == nch - 2 ? 1u : 0u);
-        R.pad = (i == nch - 1) ? 1u : 0u;  // trace: the layer's last chunk
+        R.n_acc = issue_n_acc(i, nch);
+        R.w_block = (uint32_t)(L.first_block + (c >= 0 ? c : L.n_act_chunks) * L.n_halves);
+        R.w_bytes = (uint32_t)L.n_halves * kBlockBytes;
       }
       if (L.n_act_chunks) ++cons;
     }
     T.n = j;
-    T.a_tile_odd = (uint32_t)(cons & 1);
     T.last_acc_off = bar(Bars<true>::acc_full, Bars<false>::acc_full) + 8 * ((n_gemm - 1) & 1);
     T.last_acc_n = 0;
     for (int g = 0; g < n_gemm; ++g)

@@ -1,0 +1,158 @@
+// Shared machinery of the tensor-memory-resident MLP kernels (mlp_fwd2.cu, mlp_bwd2.cu):
+// the per-tile chunk table, the two alternating MMA-issuer warps and the weight producers.
+//
+// What the hardware dictated (tools/mma_bench.cu, tools/l2_bench.cu, measured on B200):
+//  * a tcgen05.mma blocks at issue until the previous MMA has (nearly) finished and the
+//    tensor pipe idles whenever no MMA is waiting at that point; M=128 N=256 K=16 runs at
+//    128 cycles when the issue stream is dense enough.  One warp cannot do a chunk's
+//    bookkeeping (operand waits, descriptors, commits: 400+ cycles of dependent
+//    uniform-datapath instructions) inside the 512 cycles of its four MMAs, so TWO warps
+//    alternate chunks and pass a token right after their last MMA issue.
+//  * operands of tcgen05 instructions must be provably warp-uniform or the compiler wraps
+//    every instruction in an ELECT + 6x R2UR.BROADCAST waterfall: the chunk table is a
+//    __grid_constant__ kernel parameter, waits exit on warp votes, TMEM base is 0.
+//  * bulk copies issued by one thread do not overlap (~440 cycles each, any size <= 32 KB):
+//    two producer warps, 32 KB stages.
+#pragma once
+#include "common.cuh"
+#include "mlp_common.cuh"
+
+namespace fs {
+
+constexpr int kMaxChunks2 = 64;          // K chunks per tile in the issue table
+constexpr int kMmaWarps = 2;             // MMA issuers, alternating K chunks
+constexpr int kProdWarps = 2;            // weight producers, alternating stages
+constexpr int kStageBytes = 2 * kBlockBytes;  // one [256 x 64] bf16 operand stage
+
+// record flags
+constexpr uint32_t kRecDcol = 0x100u;        // accumulator region: TMEM column offset 0 / 256
+constexpr uint32_t kRecTmem = 1u << 16;      // A operand from tensor memory (else an smem SW128 tile)
+constexpr uint32_t kRecFirst = 1u << 17;     // first chunk of its layer: overwrite the accumulator
+constexpr uint32_t kRecParTile = 1u << 18;   // operand-barrier parity toggles with the tile iteration
+constexpr uint32_t kRecParShift = 19;        // bit 19: base parity of the operand barrier
+constexpr uint32_t kRecLast = 1u << 20;      // last chunk of its layer (trace only)
+
+// One record per 64-wide K chunk of a tile, in consumption order.  The table is a kernel
+// parameter so the issuing warps read it with uniform loads.
+struct IssueRec {
+  uint32_t flags;    // kRec* | layer << 24
+  uint32_t idesc;
+  uint32_t a0;       // TMEM column of the chunk's A operand, or smem byte offset of the A tile
+  uint32_t abar;     // smem byte offset of the operand-ready barrier
+  uint32_t xbar;     // smem byte offset of an "A tile free" barrier to commit after the chunk (0: none)
+  uint32_t accbar;   // smem byte offset of the accumulator-full barrier
+  uint32_t n_acc;    // how many times to commit it after this chunk (it expects one commit per issuer)
+  uint32_t w_block;  // first 16 KB block of the chunk's B operand in the packed image
+  uint32_t w_bytes;  // bytes of that operand (32 KB for N = 256, 16 KB for N = 128)
+  uint32_t pad[3];
+};
+struct IssueTable {
+  int n;
+  uint32_t last_acc_off;  // accumulator-full barrier of the tile's last layer (smem byte offset)
+  uint32_t last_acc_n;    // layers per tile sharing that barrier
+  uint32_t pad;
+  IssueRec rec[kMaxChunks2];
+};
+
+// Host side: accumulator-full commits.  Chunks alternate between the two issuers, so the
+// last chunk's issuer commits once and the previous chunk's issuer once; the issuer of a
+// single-chunk layer commits twice.
+inline uint32_t issue_n_acc(int i, int nch) {
+  return (i == nch - 1) ? (nch == 1 ? 2u : 1u) : (i == nch - 2 ? 1u : 0u);
+}
+
+struct IssueBars {
+  uint32_t w_full, w_empty, token;  // smem addresses: [kStages], [kStages], [2]
+  uint32_t ring;                    // smem address of the operand ring
+};
+
+// ------------------------------------------------------------------ weight producers
+// Producer `me` of kProdWarps streams every kProdWarps-th stage: L2 -> smem, one bulk copy.
+template <int kStages>
+__device__ __forceinline__ void producer_loop(const IssueTable& tab, const IssueBars& B, const uint8_t* packed,
+                                              int64_t n_tiles, int me, int lane) {
+  uint32_t cnt = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int j = 0; j < tab.n; ++j, ++cnt) {
+      if ((int)(cnt % kProdWarps) != me) continue;
+      const uint32_t stage = cnt % kStages, phase = (cnt / kStages) & 1;
+      mbar_wait(B.w_empty + 8 * stage, phase ^ 1);
+      if (lane == 0) {
+        const uint32_t bytes = tab.rec[j].w_bytes;
+        mbar_arrive_expect_tx(B.w_full + 8 * stage, bytes);
+        bulk_g2s(B.ring + stage * kStageBytes, packed + (size_t)tab.rec[j].w_block * kBlockBytes, bytes,
+                 B.w_full + 8 * stage);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ------------------------------------------------------------------ MMA issuers
+// All 32 lanes of issuer `me` run this loop in lock step on provably uniform values; the
+// tcgen05 instructions are guarded so that lane 0 alone issues them.  trace: optional
+// clock64 timeline [tile iteration < 4][layer][k]: k = 0 layer reached, 1 first MMA, 2 committed.
+template <int kStages>
+__device__ __forceinline__ void issuer_loop(const IssueTable& tab, const IssueBars& B, uint32_t sbase,
+                                            int64_t n_tiles, uint32_t me, int lane, long long* trace) {
+  const uint32_t issue = (lane == 0) ? 1u : 0u;
+  const int n_rec = tab.n;
+  int64_t tile = blockIdx.x;
+  uint32_t titer = 0;
+  int j = (int)me;
+  if (j >= n_rec) { j -= n_rec; tile += gridDim.x; ++titer; }
+  uint32_t stage = me % kStages, wpar = 0, tok_par = me ? 0u : 1u;
+  const bool tr = trace != nullptr && blockIdx.x == 0 && lane == 0;
+  while (tile < n_tiles) {
+    const IssueRec& R = tab.rec[j];
+    const uint32_t flags = R.flags, idesc = R.idesc;
+    const bool is_tmem = flags & kRecTmem, first = flags & kRecFirst;
+    const uint32_t d_col = flags & kRecDcol;
+    const uint32_t g_cur = flags >> 24;
+    const uint32_t a0 = is_tmem ? R.a0 : umma_desc_lo(sbase + R.a0);
+    const uint32_t b0 = umma_desc_lo(B.ring + stage * kStageBytes);
+    const uint32_t apar = (((flags & kRecParTile) ? titer : 0u) ^ (flags >> kRecParShift)) & 1u;
+    if (tr && first && titer < 4) trace[(titer * 16 + g_cur) * 8 + 0] = clock64();
+    mbar_wait_converged(B.w_full + 8 * stage, wpar);
+    mbar_wait_converged(sbase + R.abar, apar);
+    mbar_wait_converged(B.token + 8 * me, tok_par);  // the other issuer has queued its chunk
+    tok_par ^= 1u;
+    tc_fence_after();
+    if (tr && first && titer < 4) trace[(titer * 16 + g_cur) * 8 + 1] = clock64();
+    if (is_tmem) {  // features [0,32) of the chunk at columns +0, +8; [32,64) at +32, +40
+      umma_bf16_ts_conv(d_col, a0, umma_desc_from_lo(b0), idesc, first ? 0u : 1u, issue);
+      umma_bf16_ts_conv(d_col, a0 + 8, umma_desc_from_lo(b0 + 2), idesc, 1u, issue);
+      umma_bf16_ts_conv(d_col, a0 + 32, umma_desc_from_lo(b0 + 4), idesc, 1u, issue);
+      umma_bf16_ts_conv(d_col, a0 + 40, umma_desc_from_lo(b0 + 6), idesc, 1u, issue);
+    } else {
+      umma_bf16_ss_conv(d_col, umma_desc_from_lo(a0), umma_desc_from_lo(b0), idesc, first ? 0u : 1u, issue);
+      umma_bf16_ss_conv(d_col, umma_desc_from_lo(a0 + 2), umma_desc_from_lo(b0 + 2), idesc, 1u, issue);
+      umma_bf16_ss_conv(d_col, umma_desc_from_lo(a0 + 4), umma_desc_from_lo(b0 + 4), idesc, 1u, issue);
+      umma_bf16_ss_conv(d_col, umma_desc_from_lo(a0 + 6), umma_desc_from_lo(b0 + 6), idesc, 1u, issue);
+    }
+    if (lane == 0) mbar_arrive(B.token + 8 * (me ^ 1u));  // the last MMA is queued: hand over
+    __syncwarp();
+    umma_commit_conv(B.w_empty + 8 * stage, issue);
+    if (R.xbar) umma_commit_conv(sbase + R.xbar, issue);
+    const uint32_t n_acc = R.n_acc;
+    if (n_acc) {
+      umma_commit_conv(sbase + R.accbar, issue);
+      if (n_acc > 1) umma_commit_conv(sbase + R.accbar, issue);
+      if (tr && (flags & kRecLast) && titer < 4) trace[(titer * 16 + g_cur) * 8 + 2] = clock64();
+    }
+    // next chunk of mine
+    j += kMmaWarps;
+    stage += kMmaWarps;
+    if (stage >= (uint32_t)kStages) { stage -= kStages; wpar ^= 1u; }
+    if (j >= n_rec) {
+      j -= n_rec; tile += gridDim.x;
+      // the next tile's first layer overwrites TMEM region 0, which the last layer still reads
+      // as its A operand: let the tensor pipe drain first (that barrier completes last_acc_n
+      // times per tile)
+      if (tile < n_tiles) mbar_wait_converged(sbase + tab.last_acc_off, ((titer + 1) * tab.last_acc_n - 1) & 1u);
+      ++titer;
+    }
+  }
+}
+
+}  // namespace fs
