@@ -11,6 +11,7 @@
 //   warps 14,15  weight producers
 // The seed step (d(out) -> rgb head^T -> branch-layer dpre) runs on CUDA cores in the
 // epilogue warps.
+#include <stdlib.h>
 #include "common.cuh"
 #include "mlp_common.cuh"
 #include "mlp_issue.cuh"
@@ -35,7 +36,7 @@ struct SmemB {
   static constexpr int bias = staging + 4 * kStageBufsB * kSlabBytesB;   // fp32 [kMaxLayersB][256]
   static constexpr int heads = bias + kMaxLayersB * 256 * 4;             // sigma_w[256], rgb_w[3][128]
   static constexpr int bars = heads + 640 * 4;
-  static constexpr int total = bars + 256;
+  static constexpr int total = bars + 512;
 };
 struct BarsB {
   static constexpr int w_full = SmemB::bars;
@@ -43,7 +44,9 @@ struct BarsB {
   static constexpr int a_ready = w_empty + 8 * kStagesB;  // [4]
   static constexpr int acc_full = a_ready + 8 * 4;        // [2]
   static constexpr int token = acc_full + 8 * 2;          // [2]
-  static constexpr int tmem_slot = token + 16;
+  static constexpr int slab_full = token + 16;            // [4 quarters][kStageBufsB]
+  static constexpr int slab_free = slab_full + 8 * 4 * kStageBufsB;
+  static constexpr int tmem_slot = slab_free + 8 * 4 * kStageBufsB;
 };
 
 __constant__ float c_smallB[kSmallFloats];
@@ -68,9 +71,20 @@ struct ArgsB {
   const float* d_out;
   float* grads;
   uint8_t* dstash;
+  int debug;  // tuning experiments only (FSNERF_DEBUG_FLAGS); results are wrong when non-zero
 };
 
 __device__ __forceinline__ uint4 ldg_u4(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+// h = two post-ReLU bf16 (sign bits clear): 0xFFFF in each half whose value is non-zero,
+// i.e. relu'(h) as an AND mask for a packed bf16x2 gradient
+__device__ __forceinline__ uint32_t relu_mask2(uint32_t h) {
+  // h + 0x7FFF per half sets that half's top bit iff it is non-zero (no carry: h <= 0x7F80);
+  // PRMT with sign replication spreads bit 15 over bytes 0-1 and bit 31 over bytes 2-3
+  uint32_t r;
+  asm("prmt.b32 %0, %1, 0, 0xBB99;" : "=r"(r) : "r"(h + 0x7FFF7FFFu));
+  return r;
+}
+constexpr uint32_t kNoMask = 0x3F803F80u;  // "h" of an unmasked pair (bf16 1.0, 1.0)
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -86,6 +100,8 @@ mlp_dgrad2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant
   const uint32_t bar_a_ready = sbase + BarsB::a_ready;
   const uint32_t bar_acc_full = sbase + BarsB::acc_full;
   const uint32_t bar_token = sbase + BarsB::token;
+  const uint32_t bar_slab_full = sbase + BarsB::slab_full;
+  const uint32_t bar_slab_free = sbase + BarsB::slab_free;
   const uint32_t tmem_slot = sbase + BarsB::tmem_slot;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + BarsB::tmem_slot);
   float* bias_acc = reinterpret_cast<float*>(smem + SmemB::bias);
@@ -103,6 +119,10 @@ mlp_dgrad2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant
     mbar_init(bar_acc_full + 8, kMmaWarps);
     mbar_init(bar_token, 1);
     mbar_init(bar_token + 8, 1);
+    for (int i = 0; i < 4 * kStageBufsB; ++i) {
+      mbar_init(bar_slab_full + 8 * i, 2);  // the two epilogue warps of the quarter
+      mbar_init(bar_slab_free + 8 * i, 1);  // the quarter's store warp
+    }
     fence_barrier_init();
   }
   if (warp == kWarpMmaB) {
@@ -125,20 +145,39 @@ mlp_dgrad2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant
     IssueBars IB{bar_w_full, bar_w_empty, bar_token, sbase + SmemB::ring};
     issuer_loop<kStagesB>(tab, IB, sbase, n_tiles, (uint32_t)(warp - kWarpMmaB), lane, args.trace);
   } else if (warp >= kWarpRed0) {
-    // ------------------------------------------------ reducers: bias gradients
-    // one warp per lane quarter; after the quarter's slab barrier it sums the slab's 32 rows:
-    // lane l owns features 2l, 2l+1 of the 64-feature chunk (conflict-free 4 B reads)
+    // ------------------------------------------------ store warps: dstash + bias gradients
+    // one warp per lane quarter.  Per staged slab (32 rows x 64 features of one chunk): bulk
+    // store it to the dstash image, sum its 32 rows (lane l owns features 2l, 2l+1:
+    // conflict-free 4 B reads) into the bias-gradient accumulators, and free the buffer once
+    // the bulk store has read it.  The epilogue warps never block on this.
     const int quarter = warp - kWarpRed0;
     const uint32_t stage_base = sbase + SmemB::staging + quarter * (kStageBufsB * kSlabBytesB);
     uint32_t n_staged = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      uint8_t* dstash_tile = args.dstash + (size_t)tile * prog.dstash_tile_bytes;
       for (int s = -1; s < plan.n_steps; ++s) {
         const int layer = (s < 0) ? plan.g_branch : plan.step[s].target;
         const int nchunk = (s < 0) ? 2 : 4;
+        const int doff = (s < 0) ? plan.branch_dstash_off : plan.step[s].dstash_off;
         for (int c = 0; c < nchunk; ++c, ++n_staged) {
-          const uint32_t buf = stage_base + (n_staged % kStageBufsB) * kSlabBytesB;
-          named_bar_sync(1 + quarter, 96);
+          const uint32_t b = n_staged % kStageBufsB;
+          const uint32_t buf = stage_base + b * kSlabBytesB;
+          mbar_wait(bar_slab_full + 8 * (quarter * kStageBufsB + b), (n_staged / kStageBufsB) & 1);
+          if (!(args.debug & 4)) {
+            // coalesced copy with plain loads/stores (512 B per warp instruction): the epilogue
+            // then needs no generic->async proxy fence (a MEMBAR.ALL.CTA per chunk) to hand over
+            uint4* dst = reinterpret_cast<uint4*>(dstash_tile + doff + c * kChunkBytes + quarter * kSlabBytesB);
+            uint4 t[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(t[k].x), "=r"(t[k].y), "=r"(t[k].z), "=r"(t[k].w)
+                           : "r"(buf + (k * 32 + lane) * 16));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dst[k * 32 + lane] = t[k];
+          }
           float s0 = 0.f, s1 = 0.f;
+          if (!(args.debug & 2))
 #pragma unroll 8
           for (int r = 0; r < 32; ++r) {
             uint32_t w;
@@ -150,6 +189,8 @@ mlp_dgrad2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant
           }
           atomicAdd(bias_acc + layer * 256 + 64 * c + 2 * lane, s0);
           atomicAdd(bias_acc + layer * 256 + 64 * c + 2 * lane + 1, s1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_slab_free + 8 * (quarter * kStageBufsB + b));
         }
       }
     }
@@ -159,32 +200,30 @@ mlp_dgrad2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant
     const int row = quarter * 32 + lane;
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t stage_base = sbase + SmemB::staging + quarter * (kStageBufsB * kSlabBytesB);
-    const bool issuer = half == 0 && lane == 0;
     uint32_t acc_phase[2] = {0, 0};
     uint32_t n_staged = 0;
     uint32_t titer = 0;
-    // stage the 32 bf16 of this thread (16 words) into the quarter's slab, hand it to the
-    // reducer and to the bulk store (SW128 image: unit u of row r at r*128 + ((u ^ (r&7)) << 4))
-    auto stage_out = [&](const uint32_t (&w)[16], uint8_t* dst) {
-      const uint32_t buf = stage_base + (n_staged % kStageBufsB) * kSlabBytesB;
+    // stage the 32 bf16 of this thread (16 words) into the quarter's slab and hand it to the
+    // store warp (SW128 image: unit u of row r at r*128 + ((u ^ (r&7)) << 4))
+    auto stage_wait = [&]() {  // the buffer of the upcoming slab has been drained (3 slabs ago)
+      const uint32_t b = n_staged % kStageBufsB;
+      mbar_wait(bar_slab_free + 8 * (quarter * kStageBufsB + b), ((n_staged / kStageBufsB) & 1) ^ 1);
+    };
+    auto stage_out = [&](const uint32_t (&w)[16]) {
+      const uint32_t b = n_staged % kStageBufsB;
+      const uint32_t buf = stage_base + b * kSlabBytesB;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         st_shared_v4(buf + lane * 128 + (((uint32_t)(4 * half + j) ^ (uint32_t)(lane & 7)) << 4), w[4 * j],
                      w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-      fence_proxy_async_smem();
-      if (issuer) bulk_wait_read1();  // slabs older than the previous one have been read
-      named_bar_sync(1 + quarter, 96);
-      if (issuer) {
-        bulk_s2g(dst, buf, kSlabBytesB);
-        bulk_commit();
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_slab_full + 8 * (quarter * kStageBufsB + b));  // release: stores visible
       ++n_staged;
     };
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
       const int64_t p = tile * kTileM + row;
       const bool valid = p < args.n_samples;
       const uint8_t* stash_tile = args.stash + (size_t)tile * prog.stash_tile_bytes;
-      uint8_t* dstash_tile = args.dstash + (size_t)tile * prog.dstash_tile_bytes;
       // ---- seed: d(out) -> rgb head^T -> d(pre-activation) of the branch layer (128 wide)
       float dz[3] = {0.f, 0.f, 0.f}, dsig = 0.f;
       if (valid) {
@@ -204,6 +243,7 @@ mlp_dgrad2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant
           const int c0 = 64 * c + 32 * half;
 #pragma unroll
           for (int j = 0; j < 4; ++j) m[j] = ldg_u4(hb + c * kChunkBytes + sw128_off(row, my_units + j));
+          stage_wait();
           if (half == 0 && plan.n_steps > 0 && plan.step[0].mask_off >= 0)
             prefetch_l2(stash_tile + plan.step[0].mask_off + c * kChunkBytes + row * 128);
           uint32_t w[16];
@@ -214,11 +254,9 @@ mlp_dgrad2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int i = 8 * j + 2 * q;
-              float v0 = dz[0] * wr[i] + dz[1] * wr[128 + i] + dz[2] * wr[256 + i];
-              float v1 = dz[0] * wr[i + 1] + dz[1] * wr[128 + i + 1] + dz[2] * wr[256 + i + 1];
-              if ((mw[q] & 0x00007FFFu) == 0u) v0 = 0.f;  // relu'(h): h == 0 <=> masked
-              if ((mw[q] & 0x7FFF0000u) == 0u) v1 = 0.f;
-              w[4 * j + q] = pack_bf16x2(v0, v1);
+              const float v0 = dz[0] * wr[i] + dz[1] * wr[128 + i] + dz[2] * wr[256 + i];
+              const float v1 = dz[0] * wr[i + 1] + dz[1] * wr[128 + i + 1] + dz[2] * wr[256 + i + 1];
+              w[4 * j + q] = pack_bf16x2(v0, v1) & relu_mask2(mw[q]);  // relu'(h): h == 0 <=> masked
             }
           }
           // step 0 reads its A operand from region 1
@@ -227,7 +265,7 @@ mlp_dgrad2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_a_ready + 8 * c);
-          stage_out(w, dstash_tile + plan.branch_dstash_off + c * kChunkBytes + quarter * kSlabBytesB);
+          stage_out(w);
         }
       }
       // ---- chain
@@ -236,49 +274,59 @@ mlp_dgrad2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant
         const int r = s & 1;
         const uint32_t region = tmem_lane + (uint32_t)r * 256u;
         const bool last = (s == plan.n_steps - 1);
-        const uint8_t* mimg = (S.mask_off >= 0) ? stash_tile + S.mask_off : nullptr;
+        const uint8_t* mimg = (S.mask_off >= 0 && !(args.debug & 1)) ? stash_tile + S.mask_off : nullptr;
         const uint8_t* mnext = (!last && plan.step[s + 1].mask_off >= 0) ? stash_tile + plan.step[s + 1].mask_off : nullptr;
         const bool add_sigma = S.add_sigma != 0;
         // chunk 0's mask does not depend on the MMAs: fetch it before waiting on the accumulator
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          m[j] = mimg ? ldg_u4(mimg + sw128_off(row, my_units + j)) : make_uint4(~0u, ~0u, ~0u, ~0u);
+          m[j] = mimg ? ldg_u4(mimg + sw128_off(row, my_units + j)) : make_uint4(kNoMask, kNoMask, kNoMask, kNoMask);
         if (threadIdx.x == 0 && args.trace && blockIdx.x == 0 && titer < 4) args.trace[(titer * 16 + s) * 8 + 3] = clock64();
         mbar_wait(bar_acc_full + 8 * r, acc_phase[r]);
         acc_phase[r] ^= 1;
         tc_fence_after();
         if (threadIdx.x == 0 && args.trace && blockIdx.x == 0 && titer < 4) args.trace[(titer * 16 + s) * 8 + 4] = clock64();
+#define FS_TD(k_) do { if (args.trace && threadIdx.x == 0 && blockIdx.x == 0 && titer == 1 && s < 4) args.trace[512 + ((s * 4 + c) * 8) + (k_)] = clock64(); } while (0)
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           const int c0 = 64 * c + 32 * half;
           uint32_t v[32];
+          FS_TD(0);
           tmem_ld32(region + c0, v);
           // next chunk's mask (one chunk ahead), next step's mask lines into L2
           uint4 mn[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             mn[j] = (mimg && c < 3) ? ldg_u4(mimg + (c + 1) * kChunkBytes + sw128_off(row, my_units + j))
-                                    : make_uint4(~0u, ~0u, ~0u, ~0u);
+                                    : make_uint4(kNoMask, kNoMask, kNoMask, kNoMask);
           if (half == 0 && mnext) prefetch_l2(mnext + c * kChunkBytes + row * 128);
+          FS_TD(1);
+          stage_wait();
+          FS_TD(2);
           tmem_ld_wait();
+          FS_TD(3);
           uint32_t w[16];
           const float* ws = heads + c0;
+          if (add_sigma) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 w4 = *reinterpret_cast<const float4*>(ws + 4 * i);
+              v[4 * i] = __float_as_uint(fmaf(dsig, w4.x, __uint_as_float(v[4 * i])));
+              v[4 * i + 1] = __float_as_uint(fmaf(dsig, w4.y, __uint_as_float(v[4 * i + 1])));
+              v[4 * i + 2] = __float_as_uint(fmaf(dsig, w4.z, __uint_as_float(v[4 * i + 2])));
+              v[4 * i + 3] = __float_as_uint(fmaf(dsig, w4.w, __uint_as_float(v[4 * i + 3])));
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t mw[4] = {m[j].x, m[j].y, m[j].z, m[j].w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int i = 8 * j + 2 * q;
-              float v0 = __uint_as_float(v[i]), v1 = __uint_as_float(v[i + 1]);
-              if (add_sigma) {
-                v0 = fmaf(dsig, ws[i], v0);
-                v1 = fmaf(dsig, ws[i + 1], v1);
-              }
-              if ((mw[q] & 0x00007FFFu) == 0u) v0 = 0.f;
-              if ((mw[q] & 0x7FFF0000u) == 0u) v1 = 0.f;
-              w[4 * j + q] = pack_bf16x2(v0, v1);
+              w[4 * j + q] = pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])) & relu_mask2(mw[q]);
             }
           }
+          FS_TD(4);
           if (!last) {
             tmem_st16(region + c0, w);
             tmem_st_wait();
@@ -286,14 +334,15 @@ mlp_dgrad2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_a_ready + 8 * c);
           }
-          stage_out(w, dstash_tile + S.dstash_off + c * kChunkBytes + quarter * kSlabBytesB);
+          FS_TD(5);
+          stage_out(w);
+          FS_TD(6);
 #pragma unroll
           for (int j = 0; j < 4; ++j) m[j] = mn[j];
         }
         if (threadIdx.x == 0 && args.trace && blockIdx.x == 0 && titer < 4) args.trace[(titer * 16 + s) * 8 + 5] = clock64();
       }
     }
-    if (issuer) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -371,6 +420,11 @@ int mlp_dgrad_v2(const MlpProgram& P, const void* packed, int64_t n_samples, con
   a.stash = reinterpret_cast<const uint8_t*>(stash);
   a.out = out; a.d_out = d_out; a.grads = grads;
   a.dstash = reinterpret_cast<uint8_t*>(workspace);
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("FSNERF_DEBUG_FLAGS"); dbg = e ? atoi(e) : 0; }
+    a.debug = dbg;
+  }
   const int64_t n_tiles = (n_samples + kTileM - 1) / kTileM;
   const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
   cudaError_t e = cudaMemcpyToSymbolAsync(c_smallB, a.packed + P.small_off, kSmallFloats * sizeof(float), 0,
