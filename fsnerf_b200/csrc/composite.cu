@@ -145,7 +145,7 @@ composite_fwd_kernel(int64_t n_rays, int S, const float4* __restrict__ raw,
 //   product form:  dL/dsd_i = (1-a_i) * (g_i*T_i - sum_{j>i} g_j w_j / (1-a_i+1e-10))
 // The whole ray is held in registers (NB blocks); S > 32*NB is rejected host-side.
 template <int NB>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (NB <= 6) ? 3 : 1)
 composite_bwd_kernel(int64_t n_rays, int S, const float4* __restrict__ raw,
                      const float* __restrict__ ts, const float* __restrict__ te,
                      const float* __restrict__ dscale, const float* __restrict__ bkgd, int flags,
@@ -242,7 +242,104 @@ composite_bwd_kernel(int64_t n_rays, int S, const float4* __restrict__ raw,
     }
     float dsig = dsd * delta[b];
     if (relu && c[b].w <= 0.f) dsig = 0.f;
-    if (s < S) d_raw[base + s] = make_float4(w * gr, w * gg, w * gb, dsig);
+    if (s < S) __stcs(d_raw + base + s, make_float4(w * gr, w * gg, w * gb, dsig));  // write-once stream
+  }
+}
+
+// Streaming backward for the exp-sum transmittance (the reference semantics and every flag
+// combination without FSNERF_COMP_PRODUCT_TRANS).  Two passes over the ray instead of holding
+// it in registers: pass A is the forward scan (per-block carry-ins, opacity and depth sums),
+// pass B walks the blocks backwards, re-reads them (L1/L2 hits: a ray is 4.6 KB), recomputes
+// T with the SAME prefix arithmetic as the forward kernel and runs the suffix scan.  Small
+// register state -> 2x the resident warps of the register-resident kernel -> HBM stays busy.
+template <int NB>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
+composite_bwd_stream_kernel(int64_t n_rays, int S, const float4* __restrict__ raw,
+                            const float* __restrict__ ts, const float* __restrict__ te,
+                            const float* __restrict__ dscale, const float* __restrict__ bkgd, int flags,
+                            const float* __restrict__ d_rgb, const float* __restrict__ d_opacity,
+                            const float* __restrict__ d_depth, const float* __restrict__ d_weights,
+                            float4* __restrict__ d_raw, float* __restrict__ d_bkgd) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= n_rays) return;
+  const int64_t base = r * S;
+  const float ds = dscale ? dscale[r] : 1.0f;
+  const bool relu = flags & FSNERF_COMP_SIGMA_RELU;
+  float cin[NB];
+  float carry = 0.f, acc_w = 0.f, acc_d = 0.f;
+  // ---- pass A: forward scan
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    cin[b] = carry;
+    if (b * 32 >= S) continue;  // warp-uniform
+    const int s = b * 32 + lane;
+    float sd = 0.f, tmid = 0.f;
+    if (s < S) {
+      const float sigma = __ldg(reinterpret_cast<const float*>(raw + base + s) + 3);
+      const float t0 = __ldg(ts + base + s), t1 = __ldg(te + base + s);
+      sd = (relu ? fmaxf(sigma, 0.f) : sigma) * ((t1 - t0) * ds);
+      tmid = (t0 + t1) * 0.5f;
+    }
+    const float incl = warp_incl_scan_add(sd, lane);
+    const float T = expf(-(carry + (incl - sd)));
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+    const float w = T * (1.0f - expf(-sd));
+    if (s < S) {
+      acc_w += w;
+      acc_d += w * tmid;
+    }
+  }
+  acc_w = warp_sum(acc_w);
+  acc_d = warp_sum(acc_d);
+  const float gr = d_rgb[r * 3], gg = d_rgb[r * 3 + 1], gb = d_rgb[r * 3 + 2];
+  const float gA = d_opacity ? d_opacity[r] : 0.f;
+  const float gD = d_depth ? d_depth[r] : 0.f;
+  float dA = gA, dDn = gD;
+  if (!(flags & FSNERF_COMP_DEPTH_UNNORM)) {
+    const float den = fmaxf(acc_w, kEpsF32);
+    dDn = gD / den;
+    if (acc_w > kEpsF32) dA -= gD * acc_d / (den * den);
+  }
+  if (bkgd) {
+    const float dot = gr * bkgd[0] + gg * bkgd[1] + gb * bkgd[2];
+    dA -= dot;
+    if (d_bkgd && lane == 0) {
+      const float om = 1.0f - acc_w;
+      atomicAdd(d_bkgd + 0, gr * om);
+      atomicAdd(d_bkgd + 1, gg * om);
+      atomicAdd(d_bkgd + 2, gb * om);
+    }
+  }
+  // ---- pass B: backward over the blocks
+  float suffix_carry = 0.f;  // sum over later blocks of g_j w_j
+#pragma unroll
+  for (int b = NB - 1; b >= 0; --b) {
+    if (b * 32 >= S) continue;
+    const int s = b * 32 + lane;
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    float delta = 0.f, tmid = 0.f, dwv = 0.f;
+    if (s < S) {
+      c = __ldg(raw + base + s);
+      const float t0 = __ldg(ts + base + s), t1 = __ldg(te + base + s);
+      delta = (t1 - t0) * ds;
+      tmid = (t0 + t1) * 0.5f;
+      if (d_weights) dwv = ld_stream_f(d_weights + base + s);
+    }
+    const float sd = (relu ? fmaxf(c.w, 0.f) : c.w) * delta;
+    const float alpha = 1.0f - expf(-sd);
+    const float incl_sd = warp_incl_scan_add(sd, lane);
+    const float T = expf(-(cin[b] + (incl_sd - sd)));
+    const float w = T * alpha;
+    const float g = gr * c.x + gg * c.y + gb * c.z + dA + dDn * tmid + dwv;
+    const float gw = (s < S) ? g * w : 0.f;
+    const float incl = warp_suffix_scan_add(gw, lane);
+    const float later = suffix_carry + (incl - gw);  // strictly after s
+    suffix_carry += __shfl_sync(0xffffffffu, incl, 0);
+    const float dsd = g * (T - w) - later;  // T_{i+1} = T_i (1-alpha_i) = T_i - w_i
+    float dsig = dsd * delta;
+    if (relu && c.w <= 0.f) dsig = 0.f;
+    if (s < S) __stcs(d_raw + base + s, make_float4(w * gr, w * gg, w * gb, dsig));  // write-once stream
   }
 }
 
@@ -296,6 +393,19 @@ extern "C" int fsnerf_composite_backward(int64_t n_rays, int n_samples, const fl
       n_rays, n_samples, raw4, t_starts, t_ends, delta_scale, bkgd, flags, d_rgb, d_opacity,     \
       d_depth, d_weights, d_raw4, d_bkgd)
   FsProfScope prof_("composite_bwd", stream);
+#define LAUNCH_STREAM(NB)                                                                        \
+  composite_bwd_stream_kernel<NB><<<blocks, kWarpsPerBlock * 32, 0, st>>>(                       \
+      n_rays, n_samples, raw4, t_starts, t_ends, delta_scale, bkgd, flags, d_rgb, d_opacity,     \
+      d_depth, d_weights, d_raw4, d_bkgd)
+  if (!(flags & FSNERF_COMP_PRODUCT_TRANS)) {
+    if (n_samples <= 64) LAUNCH_STREAM(2);
+    else if (n_samples <= 128) LAUNCH_STREAM(4);
+    else if (n_samples <= 192) LAUNCH_STREAM(6);
+    else if (n_samples <= 256) LAUNCH_STREAM(8);
+    else LAUNCH_STREAM(16);
+    return fsnerf_check_launch("composite_backward");
+  }
+#undef LAUNCH_STREAM
   if (n_samples <= 64) LAUNCH(2);
   else if (n_samples <= 128) LAUNCH(4);
   else if (n_samples <= 192) LAUNCH(6);
