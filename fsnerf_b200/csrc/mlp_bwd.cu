@@ -345,7 +345,7 @@ mlp_wgrad_kernel(const __grid_constant__ WgradPlan plan, const __grid_constant__
   if ((sbase & 1023u) != 0) __trap();
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWStages; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_full + 8 * s, 4);   // four producer warps
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_acc_full, 1);
@@ -362,9 +362,13 @@ mlp_wgrad_kernel(const __grid_constant__ WgradPlan plan, const __grid_constant__
   const int n_mh = J.a_chunks / 2;
 
   if (t1 > t0) {
-    if (warp == 0) {
+    if (warp >= 2) {
+      // four producer warps (the epilogue warps, idle during the main loop): bulk copies issued
+      // by one thread do not overlap (tools/l2_bench.cu), so each stage's 4 KB slab copies are
+      // spread over four issuing threads, each arming the stage barrier for its own bytes
+      const int pw = warp - 2;
+      const int n_cp = J.a_chunks + J.b_chunks;
       uint32_t cnt = 0;
-      const uint32_t bytes = (uint32_t)(J.a_chunks + J.b_chunks) * kSlabBytes;
       for (int64_t tile = t0; tile < t1; ++tile) {
         const uint8_t* a_img = args.dstash + (size_t)tile * args.dstash_tile_bytes + J.a_off;
         const uint8_t* b_img = args.stash + (size_t)tile * args.stash_tile_bytes + J.b_off;
@@ -373,13 +377,17 @@ mlp_wgrad_kernel(const __grid_constant__ WgradPlan plan, const __grid_constant__
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           if (lane == 0) {
             const uint32_t sa = sbase + stage * kWStageBytes, sb = sa + 4 * kSlabBytes;
-            mbar_arrive_expect_tx(bar_full + 8 * stage, bytes);
-            for (int c = 0; c < J.a_chunks; ++c)
-              bulk_g2s(sa + c * kSlabBytes, a_img + c * kChunkBytes + slab * kSlabBytes, kSlabBytes,
-                       bar_full + 8 * stage);
-            for (int c = 0; c < J.b_chunks; ++c)
-              bulk_g2s(sb + c * kSlabBytes, b_img + c * kChunkBytes + slab * kSlabBytes, kSlabBytes,
-                       bar_full + 8 * stage);
+            int mine = 0;
+            for (int c = pw; c < n_cp; c += 4) ++mine;
+            mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)mine * kSlabBytes);
+            for (int c = pw; c < n_cp; c += 4) {
+              if (c < J.a_chunks)
+                bulk_g2s(sa + c * kSlabBytes, a_img + c * kChunkBytes + slab * kSlabBytes, kSlabBytes,
+                         bar_full + 8 * stage);
+              else
+                bulk_g2s(sb + (c - J.a_chunks) * kSlabBytes, b_img + (c - J.a_chunks) * kChunkBytes + slab * kSlabBytes,
+                         kSlabBytes, bar_full + 8 * stage);
+            }
           }
           __syncwarp();
         }
@@ -411,7 +419,8 @@ mlp_wgrad_kernel(const __grid_constant__ WgradPlan plan, const __grid_constant__
       }
       if (lane == 0) umma_commit(bar_acc_full);
       __syncwarp();
-    } else {
+    }
+    if (warp >= 2) {
       const int quarter = warp & 3;
       mbar_wait(bar_acc_full, 0);
       tc_fence_after();
@@ -457,7 +466,8 @@ mlp_heads_wgrad_kernel(const __grid_constant__ HeadsArgs a) {
   __shared__ float red[8][32][33];
   const int t = threadIdx.x, u = t & 31, rg = t >> 5;
   const int chunk = u >> 3, unit = u & 7;
-  float acc_s[8], acc_r[3][8], acc_b = 0.f;
+  float acc_s[8], acc_r[3][8];
+  float4 acc_b = make_float4(0.f, 0.f, 0.f, 0.f);  // bias sums: lane 0 of each row group
 #pragma unroll
   for (int e = 0; e < 8; ++e) { acc_s[e] = 0.f; acc_r[0][e] = acc_r[1][e] = acc_r[2][e] = 0.f; }
   for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -476,36 +486,37 @@ mlp_heads_wgrad_kernel(const __grid_constant__ HeadsArgs a) {
     __syncthreads();
     const uint8_t* rec = a.stash + (size_t)tile * a.stash_tile_bytes;
     const uint8_t* h = rec + a.h_off + chunk * kChunkBytes;
-    const uint8_t* hb = rec + a.hb_off + chunk * kChunkBytes;
-#pragma unroll 4
-    for (int rr = 0; rr < kTileM / 8; ++rr) {
-      const int r = rg * (kTileM / 8) + rr;
-      const float4 d = dsm[r];
-      const uint32_t off = sw128_off(r, unit);
-      const uint4 hv = ldg_u4(h + off);
-      const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+    // lanes with u >= 16 have no hb column: they re-read a valid unit (same cache lines as
+    // lanes 0..15) and their rgb partial sums are never used, so the loop stays branch-free
+    // and every load of a batch is in flight before the first use
+    const uint8_t* hb = rec + a.hb_off + (chunk & 1) * kChunkBytes;
+    constexpr int kBatch = 8;
+#pragma unroll 1
+    for (int r0 = 0; r0 < kTileM / 8; r0 += kBatch) {
+      uint4 hv[kBatch], bv[kBatch];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        acc_s[2 * q] = fmaf(d.w, bf16_lo(hw[q]), acc_s[2 * q]);
-        acc_s[2 * q + 1] = fmaf(d.w, bf16_hi(hw[q]), acc_s[2 * q + 1]);
+      for (int k = 0; k < kBatch; ++k) {
+        const int r = rg * (kTileM / 8) + r0 + k;
+        const uint32_t off = sw128_off(r, unit);
+        hv[k] = ldg_u4(h + off);
+        bv[k] = ldg_u4(hb + off);
       }
-      if (u < 16) {
-        const uint4 bv = ldg_u4(hb + off);
-        const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) {
+        const int r = rg * (kTileM / 8) + r0 + k;
+        const float4 d = dsm[r];
+        if (u == 0) { acc_b.x += d.x; acc_b.y += d.y; acc_b.z += d.z; acc_b.w += d.w; }
+        const uint32_t hw[4] = {hv[k].x, hv[k].y, hv[k].z, hv[k].w};
+        const uint32_t bw[4] = {bv[k].x, bv[k].y, bv[k].z, bv[k].w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+          acc_s[2 * q] = fmaf(d.w, bf16_lo(hw[q]), acc_s[2 * q]);
+          acc_s[2 * q + 1] = fmaf(d.w, bf16_hi(hw[q]), acc_s[2 * q + 1]);
           const float x0 = bf16_lo(bw[q]), x1 = bf16_hi(bw[q]);
           acc_r[0][2 * q] = fmaf(d.x, x0, acc_r[0][2 * q]); acc_r[0][2 * q + 1] = fmaf(d.x, x1, acc_r[0][2 * q + 1]);
           acc_r[1][2 * q] = fmaf(d.y, x0, acc_r[1][2 * q]); acc_r[1][2 * q + 1] = fmaf(d.y, x1, acc_r[1][2 * q + 1]);
           acc_r[2][2 * q] = fmaf(d.z, x0, acc_r[2][2 * q]); acc_r[2][2 * q + 1] = fmaf(d.z, x1, acc_r[2][2 * q + 1]);
         }
-      }
-    }
-    if (t >= 128 && t < 132) {  // bias sums: 4 threads, one component each
-      const int comp = t - 128;
-      for (int r = 0; r < kTileM; ++r) {
-        const float4 d = dsm[r];
-        acc_b += comp == 0 ? d.x : comp == 1 ? d.y : comp == 2 ? d.z : d.w;
       }
     }
   }
@@ -532,8 +543,12 @@ mlp_heads_wgrad_kernel(const __grid_constant__ HeadsArgs a) {
       }
     }
   }
-  if (t >= 128 && t < 131) atomicAdd(a.g_rgb_b + (t - 128), acc_b);
-  if (t == 131) atomicAdd(a.g_sigma_b, acc_b);
+  if (u == 0) {
+    atomicAdd(a.g_rgb_b + 0, acc_b.x);
+    atomicAdd(a.g_rgb_b + 1, acc_b.y);
+    atomicAdd(a.g_rgb_b + 2, acc_b.z);
+    atomicAdd(a.g_sigma_b, acc_b.w);
+  }
 }
 
 }  // namespace
@@ -629,7 +644,7 @@ extern "C" int fsnerf_mlp_backward(const fsnerf_net_cfg* cfg, const float* param
   ha.n_samples = n_samples; ha.n_tiles = n_tiles; ha.out = out; ha.d_out = d_out;
   ha.g_sigma_w = grads + P.sigma_w_off; ha.g_sigma_b = grads + P.sigma_b_off;
   ha.g_rgb_w = grads + P.rgb_w_off; ha.g_rgb_b = grads + P.rgb_b_off;
-  int hgrid = (int)(n_tiles < 4 * kNumSMs ? n_tiles : 4 * kNumSMs);
+  int hgrid = (int)(n_tiles < 6 * kNumSMs ? n_tiles : 6 * kNumSMs);
   {
     FsProfScope prof_("mlp_heads_wgrad", stream);
     mlp_heads_wgrad_kernel<<<hgrid, 256, 0, st>>>(ha);
@@ -661,14 +676,29 @@ extern "C" int fsnerf_mlp_backward(const fsnerf_net_cfg* cfg, const float* param
       ++WP.n_jobs;
     }
   }
-  int begin = 0;
+  // CTAs per job proportional to the bytes it streams; the kernel ends with its slowest job, so
+  // the CTAs left over by rounding go, one at a time, to the job with the most bytes per CTA
+  int n_cta[kMaxGemm + 4], used = 0;
   for (int jn = 0; jn < WP.n_jobs; ++jn) {
     int n = (int)(kNumSMs * cost[jn] / total);
     if (n < 1) n = 1;
     if ((int64_t)n > n_tiles) n = (int)n_tiles;
+    n_cta[jn] = n;
+    used += n;
+  }
+  while (used < kNumSMs) {
+    int best = -1;
+    for (int jn = 0; jn < WP.n_jobs; ++jn)
+      if ((int64_t)n_cta[jn] < n_tiles && (best < 0 || cost[jn] / n_cta[jn] > cost[best] / n_cta[best])) best = jn;
+    if (best < 0) break;
+    ++n_cta[best];
+    ++used;
+  }
+  int begin = 0;
+  for (int jn = 0; jn < WP.n_jobs; ++jn) {
     WP.job[jn].cta_begin = begin;
-    WP.job[jn].n_split = n;
-    begin += n;
+    WP.job[jn].n_split = n_cta[jn];
+    begin += n_cta[jn];
   }
   WP.n_ctas = begin;
   WgradArgs wa;
