@@ -111,7 +111,7 @@ def cpu_step_fn(sample_rays):
     return step
 
 
-def cpu_baseline(sample_rays=256, steps=3, warmup=1):
+def cpu_baseline(sample_rays=512, steps=16, warmup=1):
     step = cpu_step_fn(sample_rays)
     for _ in range(warmup):
         step()
@@ -129,7 +129,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 256
+    sample = 512
     base, dt = cpu_baseline(sample, steps=max(1, args.steps), warmup=max(1, args.warmup))
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "rays/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
@@ -138,7 +138,7 @@ def run_reference(args):
             "e2e": {"value": base["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference arm = the reference's PyTorch NeRF math on the host CPU (oracle port: the "
                     "reference itself cannot run here, its sampler/compositor nerfacc 0.5.3 is not installable); "
-                    "each step is a bounded 256-ray sample of the 4096-ray workload step"}
+                    "each step is a bounded 512-ray sample of the 4096-ray workload step"}
     print(json.dumps(line))
 
 
@@ -148,6 +148,23 @@ def workload_config(n):
             "rays_per_gpu": R_PER_GPU, "global_rays": R_PER_GPU * n, "n_coarse": N_COARSE, "n_fine": N_FINE,
             "parallelism": f"dp{n} (ray-sharded, one NCCL all-reduce of the flat fp32 gradient)" if n > 1 else "single GPU",
             "l2": "per-step working set (>9 GB of activation stash) exceeds the 126 MB L2; no explicit flush"}
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` (mean over the launches
+    of one step) from the newest committed `ncu --set full` capture (profiles/*_traffic.json,
+    written by tools/ncu_table.py); None when there is no capture of that kernel."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    key = {"mlp_fwd_train": "mlp_fwd"}.get(kernel, kernel)
+    rows = [r for k, v in d.items() if k.startswith(key) for r in v]
+    if not rows:
+        return None, None
+    return (sum(r["dram_read_bytes"] + r["dram_write_bytes"] for r in rows) / len(rows),
+            os.path.relpath(files[-1], ROOT) + f" ({len(rows)} launches)")
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -177,7 +194,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
+        os.environ.pop("NCCL_DEBUG", None)  # NCCL_DEBUG>=VERSION prints a banner on stdout; keep it to the ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     ops.require_device(local)
     W_ = max(3, args.warmup)
@@ -358,8 +375,10 @@ def main():
     dom = max((k for k in prof if k in flops), key=lambda k: prof[k][0])
     dom_ms_per_step = prof[dom][0] / K
     achieved = flops[dom] / (dom_ms_per_step / 1e3) / 1e12
+    traffic, traffic_src = ncu_traffic(dom)
     roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": pk["tf_sus"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tf_sus"], "traffic": None, "peak_source": pk["src"] + " (sustained bf16)",
+                "frac": achieved / pk["tf_sus"], "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": pk["src"] + " (sustained bf16)",
                 "launches_per_step": prof[dom][1] / K, "ms_per_step": dom_ms_per_step,
                 "kernel_ms_per_step": {k: v[0] / K for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
                 "kernel_share_of_step": {k: round(s, 4) for k, s in sorted(share.items(), key=lambda kv: -kv[1])},
@@ -367,7 +386,7 @@ def main():
 
     base = None
     if not args.no_cpu_baseline:
-        base, _ = cpu_baseline(256, steps=3, warmup=1)
+        base, _ = cpu_baseline(512, steps=16, warmup=1)  # ~10-15 s of CPU work on the box's host cores
 
     line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W_,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

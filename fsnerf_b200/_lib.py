@@ -36,6 +36,8 @@ SIGNATURES = {
     "fsnerf_sample_pdf": (_i, [_l, _i, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p]),
     "fsnerf_composite_forward": (_i, [_l, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
     "fsnerf_composite_backward": (_i, [_l, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "fsnerf_composite_backward_occ": (_i, [_l, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p,
+                                          _i, _f, _f, _f, _p, _p]),
     "fsnerf_mlp_param_count": (_l, [C.POINTER(NetCfg)]),
     "fsnerf_mlp_param_layout": (_i, [C.POINTER(NetCfg), C.POINTER(_l), C.POINTER(_l), _i]),
     "fsnerf_mlp_packed_bytes": (_l, [C.POINTER(NetCfg)]),
@@ -50,6 +52,8 @@ SIGNATURES = {
     "fsnerf_profile_read": (_i, [_i, C.c_char_p, C.POINTER(_f), C.POINTER(_i)]),
     "fsnerf_debug_set_trace": (_i, [_p]),
     "fsnerf_adam_step": (_i, [_l, _p, _p, _p, _p, _f, _f, _f, _f, _i, _p]),
+    "fsnerf_adam_step_reg": (_i, [_l, _p, _p, _p, _p, _f, _f, _f, _f, _i, _i, _f, _i,
+                                 C.POINTER(_l), C.POINTER(_l), _p, _p]),
 }
 
 _lib = None

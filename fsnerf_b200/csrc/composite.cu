@@ -46,6 +46,16 @@ __device__ __forceinline__ float warp_suffix_scan_add(float v, int lane) {
   return v;
 }
 
+// Occlusion regulariser of src/core/loss.py:26-60 as called at src/run-nerf.py:260-264, fused
+// into the compositing backward: loss = mean_r sum_s w(t_mid) * sigma_raw, so
+// d(loss)/d(sigma_raw) = scale * w(t_mid) with scale = 1/(rays in the GLOBAL batch).
+// func: 0 off, 1 'linear' w = -a t + b, 2 'exp' w = a exp(-b t).  loss (may be NULL)
+// accumulates the UNSCALED sum over this launch's rays.
+struct OccReg { int func; float a, b, scale; float* loss; };
+__device__ __forceinline__ float occ_weight(const OccReg& o, float t) {
+  return o.func == 1 ? fmaf(-o.a, t, o.b) : o.a * expf(-o.b * t);
+}
+
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -151,7 +161,7 @@ composite_bwd_kernel(int64_t n_rays, int S, const float4* __restrict__ raw,
                      const float* __restrict__ dscale, const float* __restrict__ bkgd, int flags,
                      const float* __restrict__ d_rgb, const float* __restrict__ d_opacity,
                      const float* __restrict__ d_depth, const float* __restrict__ d_weights,
-                     float4* __restrict__ d_raw, float* __restrict__ d_bkgd) {
+                     float4* __restrict__ d_raw, float* __restrict__ d_bkgd, const OccReg occ) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (r >= n_rays) return;
@@ -159,6 +169,7 @@ composite_bwd_kernel(int64_t n_rays, int S, const float4* __restrict__ raw,
   const float ds = dscale ? dscale[r] : 1.0f;
   const bool relu = flags & FSNERF_COMP_SIGMA_RELU;
   const bool prod = flags & FSNERF_COMP_PRODUCT_TRANS;
+  float occ_acc = 0.f;
   float4 c[NB];
   float delta[NB], tm[NB], T[NB], al[NB], dw[NB];
   float carry = prod ? 1.0f : 0.0f;
@@ -242,7 +253,16 @@ composite_bwd_kernel(int64_t n_rays, int S, const float4* __restrict__ raw,
     }
     float dsig = dsd * delta[b];
     if (relu && c[b].w <= 0.f) dsig = 0.f;
+    if (occ.func && s < S) {
+      const float ow = occ_weight(occ, tm[b]);
+      dsig = fmaf(occ.scale, ow, dsig);
+      occ_acc = fmaf(ow, c[b].w, occ_acc);
+    }
     if (s < S) __stcs(d_raw + base + s, make_float4(w * gr, w * gg, w * gb, dsig));  // write-once stream
+  }
+  if (occ.func && occ.loss) {
+    occ_acc = warp_sum(occ_acc);
+    if (lane == 0) atomicAdd(occ.loss, occ_acc);
   }
 }
 
@@ -259,7 +279,7 @@ composite_bwd_stream_kernel(int64_t n_rays, int S, const float4* __restrict__ ra
                             const float* __restrict__ dscale, const float* __restrict__ bkgd, int flags,
                             const float* __restrict__ d_rgb, const float* __restrict__ d_opacity,
                             const float* __restrict__ d_depth, const float* __restrict__ d_weights,
-                            float4* __restrict__ d_raw, float* __restrict__ d_bkgd) {
+                            float4* __restrict__ d_raw, float* __restrict__ d_bkgd, const OccReg occ) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (r >= n_rays) return;
@@ -313,6 +333,7 @@ composite_bwd_stream_kernel(int64_t n_rays, int S, const float4* __restrict__ ra
   }
   // ---- pass B: backward over the blocks
   float suffix_carry = 0.f;  // sum over later blocks of g_j w_j
+  float occ_acc = 0.f;
 #pragma unroll
   for (int b = NB - 1; b >= 0; --b) {
     if (b * 32 >= S) continue;
@@ -339,7 +360,16 @@ composite_bwd_stream_kernel(int64_t n_rays, int S, const float4* __restrict__ ra
     const float dsd = g * (T - w) - later;  // T_{i+1} = T_i (1-alpha_i) = T_i - w_i
     float dsig = dsd * delta;
     if (relu && c.w <= 0.f) dsig = 0.f;
+    if (occ.func && s < S) {
+      const float ow = occ_weight(occ, tmid);
+      dsig = fmaf(occ.scale, ow, dsig);
+      occ_acc = fmaf(ow, c.w, occ_acc);
+    }
     if (s < S) __stcs(d_raw + base + s, make_float4(w * gr, w * gg, w * gb, dsig));  // write-once stream
+  }
+  if (occ.func && occ.loss) {
+    occ_acc = warp_sum(occ_acc);
+    if (lane == 0) atomicAdd(occ.loss, occ_acc);
   }
 }
 
@@ -372,12 +402,45 @@ extern "C" int fsnerf_composite_forward(int64_t n_rays, int n_samples, const flo
   return fsnerf_check_launch("composite_forward");
 }
 
+static int composite_backward_impl(int64_t n_rays, int n_samples, const float* raw,
+                                   const float* t_starts, const float* t_ends,
+                                   const float* delta_scale, const float* bkgd, int flags,
+                                   const float* d_rgb, const float* d_opacity,
+                                   const float* d_depth, const float* d_weights, float* d_raw,
+                                   float* d_bkgd, const OccReg occ, void* stream);
+
 extern "C" int fsnerf_composite_backward(int64_t n_rays, int n_samples, const float* raw,
                                          const float* t_starts, const float* t_ends,
                                          const float* delta_scale, const float* bkgd, int flags,
                                          const float* d_rgb, const float* d_opacity,
                                          const float* d_depth, const float* d_weights, float* d_raw,
                                          float* d_bkgd, void* stream) {
+  const OccReg occ = {0, 0.f, 0.f, 0.f, nullptr};
+  return composite_backward_impl(n_rays, n_samples, raw, t_starts, t_ends, delta_scale, bkgd, flags,
+                                 d_rgb, d_opacity, d_depth, d_weights, d_raw, d_bkgd, occ, stream);
+}
+
+extern "C" int fsnerf_composite_backward_occ(int64_t n_rays, int n_samples, const float* raw,
+                                             const float* t_starts, const float* t_ends,
+                                             const float* delta_scale, const float* bkgd, int flags,
+                                             const float* d_rgb, const float* d_opacity,
+                                             const float* d_depth, const float* d_weights,
+                                             float* d_raw, float* d_bkgd, int occ_func, float occ_a,
+                                             float occ_b, float occ_scale, float* occ_loss_sum,
+                                             void* stream) {
+  FS_REQUIRE(occ_func >= 0 && occ_func <= 2, "composite_backward_occ: occ_func must be 0 (off), 1 (linear) or 2 (exp)");
+  FS_REQUIRE(occ_a >= 0.f && occ_b >= 0.f, "composite_backward_occ: a and b should be non-negative");
+  const OccReg occ = {occ_func, occ_a, occ_b, occ_scale, occ_loss_sum};
+  return composite_backward_impl(n_rays, n_samples, raw, t_starts, t_ends, delta_scale, bkgd, flags,
+                                 d_rgb, d_opacity, d_depth, d_weights, d_raw, d_bkgd, occ, stream);
+}
+
+static int composite_backward_impl(int64_t n_rays, int n_samples, const float* raw,
+                                   const float* t_starts, const float* t_ends,
+                                   const float* delta_scale, const float* bkgd, int flags,
+                                   const float* d_rgb, const float* d_opacity,
+                                   const float* d_depth, const float* d_weights, float* d_raw,
+                                   float* d_bkgd, const OccReg occ, void* stream) {
   if (n_rays == 0) return FSNERF_OK;
   FS_REQUIRE(raw && t_starts && t_ends && d_rgb && d_raw, "composite_backward: null pointer");
   FS_REQUIRE(n_samples >= 1 && n_samples <= 512, "composite_backward: n_samples must be in [1,512]");
@@ -391,12 +454,12 @@ extern "C" int fsnerf_composite_backward(int64_t n_rays, int n_samples, const fl
 #define LAUNCH(NB)                                                                               \
   composite_bwd_kernel<NB><<<blocks, kWarpsPerBlock * 32, 0, st>>>(                              \
       n_rays, n_samples, raw4, t_starts, t_ends, delta_scale, bkgd, flags, d_rgb, d_opacity,     \
-      d_depth, d_weights, d_raw4, d_bkgd)
+      d_depth, d_weights, d_raw4, d_bkgd, occ)
   FsProfScope prof_("composite_bwd", stream);
 #define LAUNCH_STREAM(NB)                                                                        \
   composite_bwd_stream_kernel<NB><<<blocks, kWarpsPerBlock * 32, 0, st>>>(                       \
       n_rays, n_samples, raw4, t_starts, t_ends, delta_scale, bkgd, flags, d_rgb, d_opacity,     \
-      d_depth, d_weights, d_raw4, d_bkgd)
+      d_depth, d_weights, d_raw4, d_bkgd, occ)
   if (!(flags & FSNERF_COMP_PRODUCT_TRANS)) {
     if (n_samples <= 64) LAUNCH_STREAM(2);
     else if (n_samples <= 128) LAUNCH_STREAM(4);

@@ -63,6 +63,11 @@ class HotPath:
             self.world = torch.distributed.get_world_size(process_group) if process_group is not None or (
                 torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
         self.loss_sums = torch.zeros(2, device=self.device)
+        # in-step regularisers: occlusion (src/core/loss.py:26-60) fused into the
+        # compositing backward, weight-norm penalty (src/run-nerf.py:266-279) fused into Adam
+        self.occ_sum = torch.zeros(1, device=self.device)
+        self.reg_segs = ops.reg_segments(self.cfg, n_nets)
+        self.reg_sums = torch.zeros(len(self.reg_segs), device=self.device)
         self.mask_pos = self.mask_dir = None
         self._buf = {}
         self._packed_fresh = False
@@ -143,10 +148,19 @@ class HotPath:
     # --------------------------------------------------------------- train step
     @torch.no_grad()
     def train_step(self, rays_o, rays_d, rgb_gt, u_strat=None, u_pdf=None, lr: Optional[float] = None,
-                   global_rays: Optional[int] = None, apply_update: bool = True):
+                   global_rays: Optional[int] = None, apply_update: bool = True,
+                   occ_reg=None, weight_reg=None):
         """One optimisation step on this rank's ray shard.  Returns a device
         tensor [2] = (sum sq err coarse, sum sq err fine) over the local shard;
-        mean loss = value / (3 * global_rays).  u_* default to torch.rand."""
+        mean loss = value / (3 * global_rays).  u_* default to torch.rand.
+
+        occ_reg = (a, b, func): adds core.loss.OcclusionRegularizer(a, b, func) of the output
+        pass (the fine network's samples; the coarse ones when n_fine == 0) to the loss exactly
+        as src/run-nerf.py:260-264 does (NOT scaled by beta, which only gates it there);
+        self.occ_sum / global_rays is its value.  weight_reg = (mode, alpha): the weight-norm
+        penalty of src/run-nerf.py:266-279 ('l1' or Frobenius) on every network of the flat
+        buffer; the caller applies the reference's `k < int(reg_ratio*Td)` gate by passing
+        None.  self.reg_sums holds sum|w| (l1) / sum w^2 (l2) per regularised tensor."""
         cfg, R = self.cfg, rays_o.shape[0]
         G = int(global_rays) if global_rays is not None else R * self.world
         if u_strat is None:
@@ -157,9 +171,13 @@ class HotPath:
         self.loss_sums.zero_()
         self.grads.zero_()
         scale = loss_grad_scale(G)  # F.mse_loss 'mean' over the GLOBAL batch (src/run-nerf.py:256)
+        occ = None
+        if occ_reg is not None:
+            self.occ_sum.zero_()
+            occ = (occ_reg[0], occ_reg[1], occ_reg[2], 1.0 / G, self.occ_sum)
         d_rgb_c = ops.mse_loss_grad(o["rgb_c"], rgb_gt, scale, self.loss_sums[0:1])
         d_raw_c, _ = ops.composite_backward(o["raw_c"].view(R, self.n_coarse, 4), o["ts_c"], o["te_c"], d_rgb_c,
-                                            bkgd=self.bkgd)
+                                            bkgd=self.bkgd, occ=None if self.hier else occ)
         ws_c = self._bytes("ws_c", ops.mlp_bwd_workspace_bytes(cfg, R * self.n_coarse))
         ops.mlp_backward(cfg, self.net_params(0), self.packed[0], R * self.n_coarse, o["st_c"], o["raw_c"],
                          d_raw_c.view(-1, 4), self.net_grads(0), ws_c)
@@ -168,7 +186,7 @@ class HotPath:
             S = self.n_coarse + self.n_fine
             d_rgb_f = ops.mse_loss_grad(o["rgb"], rgb_gt, scale, self.loss_sums[1:2])
             d_raw_f, _ = ops.composite_backward(o["raw_f"].view(R, S, 4), o["ts_f"], o["te_f"], d_rgb_f,
-                                                bkgd=self.bkgd)
+                                                bkgd=self.bkgd, occ=occ)
             ws_f = self._bytes("ws_f", ops.mlp_bwd_workspace_bytes(cfg, R * S))
             ops.mlp_backward(cfg, self.net_params(1), self.packed[1], R * S, o["st_f"], o["raw_f"],
                              d_raw_f.view(-1, 4), self.net_grads(1), ws_f)
@@ -178,8 +196,13 @@ class HotPath:
             allreduce_gradients(self.grads, self.pg)
         if apply_update:
             self.step += 1
-            ops.adam_step(self.params, self.grads, self.m, self.v, self.lr if lr is None else lr, self.step)
-            self.launches += 1
+            if weight_reg is not None:
+                ops.adam_step_reg(self.params, self.grads, self.m, self.v, self.lr if lr is None else lr,
+                                  self.step, weight_reg[0], weight_reg[1], self.reg_segs, self.reg_sums)
+                self.launches += 2
+            else:
+                ops.adam_step(self.params, self.grads, self.m, self.v, self.lr if lr is None else lr, self.step)
+                self.launches += 1
             self._packed_fresh = False
         return self.loss_sums
 

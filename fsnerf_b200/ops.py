@@ -112,12 +112,28 @@ def composite_forward(raw, t_starts, t_ends, bkgd=None, delta_scale=None, flags=
     return rgb, op, dp, w, al, tr
 
 
+OCC_FUNCS = {"linear": 1, "exp": 2}  # core.loss.OcclusionRegularizer.func (src/core/loss.py:57-62)
+
+
 def composite_backward(raw, t_starts, t_ends, d_rgb, d_opacity=None, d_depth=None, d_weights=None,
-                       bkgd=None, delta_scale=None, flags=0, want_d_bkgd=False):
+                       bkgd=None, delta_scale=None, flags=0, want_d_bkgd=False, occ=None):
+    """occ = None, or (a, b, func, scale, loss_sum): the occlusion regulariser fused in
+    (d_raw.sigma += scale*w(t_mid); loss_sum[0] += sum w(t_mid)*sigma, unscaled)."""
     raw, ts, te = _f32c(raw, "raw"), _f32c(t_starts, "t_starts"), _f32c(t_ends, "t_ends")
     R, S = ts.shape
     d_raw = torch.empty(R, S, 4, device=raw.device)
     d_bkgd = torch.zeros(3, device=raw.device) if want_d_bkgd else None
+    if occ is not None:
+        a, b, func, scale, loss_sum = occ
+        if func not in OCC_FUNCS:
+            raise ValueError(f"Unknown occlusion regularizer type: {func}")  # loss.py:62
+        check(_lib.load().fsnerf_composite_backward_occ(
+            R, S, ptr(raw), ptr(ts), ptr(te), ptr(_f32c(delta_scale, "delta_scale")),
+            ptr(_f32c(bkgd, "bkgd")), flags, ptr(_f32c(d_rgb, "d_rgb")),
+            ptr(_f32c(d_opacity, "d_opacity")), ptr(_f32c(d_depth, "d_depth")),
+            ptr(_f32c(d_weights, "d_weights")), ptr(d_raw), ptr(d_bkgd), OCC_FUNCS[func], float(a),
+            float(b), float(scale), ptr(loss_sum), _stream()), "fsnerf_composite_backward_occ")
+        return d_raw, d_bkgd
     check(_lib.load().fsnerf_composite_backward(
         R, S, ptr(raw), ptr(ts), ptr(te), ptr(_f32c(delta_scale, "delta_scale")),
         ptr(_f32c(bkgd, "bkgd")), flags, ptr(_f32c(d_rgb, "d_rgb")),
@@ -241,6 +257,32 @@ def adam_step(params, grads, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
     check(_lib.load().fsnerf_adam_step(params.numel(), ptr(params), ptr(grads), ptr(m), ptr(v),
                                        float(lr), beta1, beta2, eps, int(step), _stream()),
           "fsnerf_adam_step")
+
+
+def reg_segments(cfg, n_nets=1):
+    """flat [begin, end) ranges of the tensors the reference's weight penalty covers:
+    '"weight" in name and param.shape[0] > 3' (src/run-nerf.py:272-273) — every weight except
+    sigma.weight [1,H] and rgb.weight [3,H/2] — for n_nets networks laid back to back."""
+    n_net = mlp_param_count(cfg)
+    segs = []
+    for i in range(n_nets):
+        for (off, numel), name in zip(mlp_param_layout(cfg), state_dict_names(cfg)):
+            if "weight" in name and name not in ("sigma.weight", "rgb.weight"):
+                segs.append((i * n_net + off, i * n_net + off + numel))
+    return segs
+
+
+def adam_step_reg(params, grads, m, v, lr, step, mode, alpha, segments, seg_sums,
+                  beta1=0.9, beta2=0.999, eps=1e-8):
+    """Adam with the weight-norm penalty fused in; mode 'l1' or anything else (Frobenius),
+    like the reference's `args.reg` switch.  seg_sums [len(segments)] device floats."""
+    n = len(segments)
+    b = (C.c_int64 * n)(*[s[0] for s in segments])
+    e = (C.c_int64 * n)(*[s[1] for s in segments])
+    check(_lib.load().fsnerf_adam_step_reg(params.numel(), ptr(params), ptr(grads), ptr(m), ptr(v),
+                                           float(lr), beta1, beta2, eps, int(step),
+                                           1 if mode == "l1" else 2, float(alpha), n, b, e,
+                                           ptr(seg_sums), _stream()), "fsnerf_adam_step_reg")
 
 
 # -------------------------------------------------------------- profiling

@@ -87,6 +87,20 @@ int fsnerf_composite_backward(int64_t n_rays, int n_samples, const float* raw,
                               const float* d_opacity, const float* d_depth, const float* d_weights,
                               float* d_raw, float* d_bkgd, void* stream);
 
+/* Same as fsnerf_composite_backward with the occlusion regulariser
+ * (core.loss.OcclusionRegularizer, src/core/loss.py:26-60, added to the loss at
+ * src/run-nerf.py:260-264) fused in:  loss_occ = mean_r sum_s w(t_mid)*sigma_raw,
+ * w = -a t + b (occ_func 1, 'linear') or a exp(-b t) (occ_func 2, 'exp');
+ * d_raw.sigma += occ_scale * w(t_mid)   (occ_scale = 1 / rays of the GLOBAL batch),
+ * *occ_loss_sum += sum_r sum_s w*sigma_raw (unscaled; NULL to skip).  occ_func 0 = off. */
+int fsnerf_composite_backward_occ(int64_t n_rays, int n_samples, const float* raw,
+                                  const float* t_starts, const float* t_ends,
+                                  const float* delta_scale, const float* bkgd, int flags,
+                                  const float* d_rgb, const float* d_opacity, const float* d_depth,
+                                  const float* d_weights, float* d_raw, float* d_bkgd, int occ_func,
+                                  float occ_a, float occ_b, float occ_scale, float* occ_loss_sum,
+                                  void* stream);
+
 /* ---- (2)+(3) NeRF MLP -------------------------------------------------- */
 /* Architecture of core.models.NeRF (src/core/models.py:57-109). */
 typedef struct fsnerf_net_cfg {
@@ -144,6 +158,20 @@ int fsnerf_mse_loss_grad(int64_t n, const float* rgb, const float* gt, float gra
 /* torch.optim.Adam (defaults) on a flat buffer; step counts from 1 */
 int fsnerf_adam_step(int64_t n, float* params, const float* grads, float* m, float* v, float lr,
                      float beta1, float beta2, float eps, int step, void* stream);
+
+/* fsnerf_adam_step with the weight-norm ("frequency") penalty of
+ * src/run-nerf.py:266-279 fused in: for every regularised tensor t (flat range
+ * [seg_begin[t], seg_end[t]) — the weights with shape[0] > 3)
+ *   reg_mode 1 ('l1'): loss += alpha*sum|w|       -> grad += alpha*sign(w)
+ *   reg_mode 2 (else): loss += alpha*||W_t||_F    -> grad += alpha*w/||W_t||_F
+ * before the Adam update.  seg_sums [n_segs] device floats (workspace AND
+ * output): sum|w| (l1) or sum w^2 (l2) per tensor, computed from the
+ * PRE-update weights.  n_segs <= 32.  Call it after the data-parallel
+ * all-reduce so that the penalty is added once. */
+int fsnerf_adam_step_reg(int64_t n, float* params, const float* grads, float* m, float* v, float lr,
+                         float beta1, float beta2, float eps, int step, int reg_mode,
+                         float reg_alpha, int n_segs, const int64_t* seg_begin,
+                         const int64_t* seg_end, float* seg_sums, void* stream);
 
 /* ---- measurement aid (bench.py): per-kernel device time ------------------ */
 /* on != 0: start recording a cudaEvent pair around every kernel this library

@@ -64,12 +64,16 @@ def render_rays_hier(sd_coarse, sd_fine, rays_o, rays_d, near, far, n_coarse,
 
 def train_step(sd_coarse, sd_fine, opt_state, rays_o, rays_d, rgb_gt, near, far,
                n_coarse, n_fine, u_strat, u_pdf, lr, white_bkgd=False,
-               mask_pos=None, mask_dir=None, betas=(0.9, 0.999), eps=1e-8, **kw):
+               mask_pos=None, mask_dir=None, betas=(0.9, 0.999), eps=1e-8,
+               occ_reg=None, weight_reg=None, **kw):
     """One optimisation step in place on the state dicts.
     loss = mse(rgb_fine, gt) [+ mse(rgb_coarse, gt) when n_fine > 0];
     Adam exactly as torch.optim.Adam defaults (src/run-nerf.py:216-217).
     opt_state: dict(step=int, m={...}, v={...}) keyed 'c.<name>' / 'f.<name>'.
+    occ_reg=(a,b,func): + OcclusionRegularizer of the output pass (src/run-nerf.py:260-264);
+    weight_reg=(mode, alpha): + alpha * weight penalty over every network (run-nerf.py:266-279).
     -> (loss, psnr_fine, grads dict)"""
+    from . import regularizers as oreg
     params = {}
     for k, v in sd_coarse.items():
         params["c." + k] = v.requires_grad_(True)
@@ -83,6 +87,11 @@ def train_step(sd_coarse, sd_fine, opt_state, rays_o, rays_d, rgb_gt, near, far,
     loss = loss_f
     if n_fine > 0:
         loss = loss + torch.nn.functional.mse_loss(out["rgb_coarse"], gt)
+    if occ_reg is not None:
+        loss = loss + oreg.occlusion_reg_dense(out["raw"][..., 3], out["t_starts"], out["t_ends"], *occ_reg)
+    if weight_reg is not None:
+        nets = [sd_coarse] + ([sd_fine] if n_fine > 0 else [])
+        loss = loss + weight_reg[1] * sum(oreg.weight_reg(sd, weight_reg[0]) for sd in nets)
     grads = torch.autograd.grad(loss, list(params.values()))
     grads = dict(zip(params.keys(), grads))
     opt_state["step"] += 1

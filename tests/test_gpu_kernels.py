@@ -298,3 +298,72 @@ def test_mlp_backward_weight_grads(dev, P, seed, scale):
     twice = _unflatten(cfg, grads)
     n0 = "layers.3.weight"
     assert ((twice[n0] - 2 * ours[n0]).norm() / (2 * ours[n0]).norm()).item() < 1e-3
+
+
+# ------------------------------------------------------------------ in-step regularisers (f2)
+@pytest.mark.gpu
+@pytest.mark.parametrize("R,S,flags,func", [(300, 192, 0, "linear"), (77, 64, 1, "exp"), (9, 33, 4, "linear"),
+                                            (5, 300, 2, "exp")])
+def test_composite_backward_with_occlusion_reg(dev, R, S, flags, func):
+    """occlusion regulariser (src/core/loss.py:26-60) fused into the compositing backward:
+    d_raw and the loss value vs autograd of oracle compositing + oracle.regularizers."""
+    from fsnerf_b200 import ops
+    from oracle import regularizers as oreg
+    raw, ts, te = _comp_inputs(R, S, seed=3 * R + S)
+    if flags & 4:
+        raw[..., 3] = raw[..., 3].abs()
+    a, b = (0.5, 2.0) if func == "linear" else (1.5, 0.7)
+    kw = dict(sigma_relu=bool(flags & 1), normalize_depth=not (flags & 2), product_trans=bool(flags & 4))
+    g = torch.Generator().manual_seed(3)
+    d_rgb = torch.randn(R, 3, generator=g)
+    raw_r = raw.clone().requires_grad_(True)
+    rgb, *_ = ocomp.composite_dense(raw_r, ts, te, None, **kw)
+    G = 4 * R  # this launch is one shard of a 4x larger global batch
+    occ = oreg.occlusion_reg_dense(raw_r[..., 3], ts, te, a, b, func) * (R / G)
+    (g_raw,) = torch.autograd.grad((rgb * d_rgb).sum() + occ, raw_r)
+    occ_sum = torch.zeros(1, device=dev)
+    d_raw, _ = ops.composite_backward(cu(raw.numpy(), dev), cu(ts.numpy(), dev), cu(te.numpy(), dev),
+                                      d_rgb.to(dev), flags=flags, occ=(a, b, func, 1.0 / G, occ_sum))
+    assert (d_raw.cpu() - g_raw).abs().max().item() <= 1e-4 * max(1.0, g_raw.abs().max().item())
+    assert abs(occ_sum.item() / G - occ.item()) <= 1e-5 * max(1.0, abs(occ.item()))
+    with pytest.raises(ValueError):
+        ops.composite_backward(cu(raw.numpy(), dev), cu(ts.numpy(), dev), cu(te.numpy(), dev), d_rgb.to(dev),
+                               occ=(a, b, "cubic", 1.0, occ_sum))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["l1", "l2"])
+def test_adam_with_weight_penalty(dev, mode):
+    """weight-norm penalty (src/run-nerf.py:266-279) fused into Adam vs torch.optim.Adam on
+    grad + alpha * d(penalty), on the reference's parameter set (golden-pinned coverage)."""
+    from fsnerf_b200 import ops
+    from oracle import regularizers as oreg
+    cfg = ops.make_cfg()
+    sd = omlp.init_state_dict(seed=42)
+    segs = ops.reg_segments(cfg, 1)
+    names = oreg.regularised_names([(k, tuple(v.shape)) for k, v in sd.items()])
+    lay = dict(zip(ops.state_dict_names(cfg), ops.mlp_param_layout(cfg)))
+    assert segs == [(lay[n][0], lay[n][0] + lay[n][1]) for n in names]
+    alpha = 1e-3
+    p = ops.flatten_state_dict(cfg, sd, dev)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    sums = torch.zeros(len(segs), device=dev)
+    ref = {k: torch.nn.Parameter(t.clone()) for k, t in sd.items()}
+    opt = torch.optim.Adam(list(ref.values()), lr=5e-4)
+    g = torch.Generator().manual_seed(1)
+    for step in range(1, 4):
+        grads = {k: 1e-3 * torch.randn(t.shape, generator=g) for k, t in sd.items()}
+        pen = oreg.weight_reg(ref, mode)
+        pg = torch.autograd.grad(alpha * pen, [ref[n] for n in names])
+        for k in ref:
+            ref[k].grad = grads[k].clone()
+        for n, gg in zip(names, pg):
+            ref[n].grad += gg
+        flat_g = ops.flatten_state_dict(cfg, grads, dev)
+        ops.adam_step_reg(p, flat_g, m, v, 5e-4, step, mode, alpha, segs, sums)
+        val = sums.sum().item() if mode == "l1" else sums.sqrt().sum().item()
+        assert abs(val - pen.item()) <= 1e-5 * pen.item()
+        opt.step()
+        ours = _unflatten(cfg, p)
+        for k in ref:
+            assert (ours[k] - ref[k].detach().reshape(-1)).abs().max().item() < 2e-6, (k, step)

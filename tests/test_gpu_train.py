@@ -243,3 +243,63 @@ def test_render_frame_and_path(dev):
     cat = np.concatenate([p[0] for p in parts], 0).reshape(3, H, W, 3)
     assert [p[2] for p in parts] == [(450 * r, 450 * (r + 1)) for r in range(4)]
     np.testing.assert_allclose(cat, frames, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Sf,mode", [(64, "l1"), (0, "l2")])
+def test_fused_train_step_with_regularisers(dev, Sf, mode):
+    """occlusion regulariser + weight penalty inside the fused step vs the oracle
+    step carrying the reference's loss terms (src/run-nerf.py:260-279); coarse-only (C1 shape)
+    and hierarchical."""
+    from fsnerf_b200.engine import HotPath
+    R, Sc = 384, 64
+    _, _, _, _, o, d, gt = _scene_rays(R, seed=9)
+    rng = np.random.default_rng(8)
+    us = rng.random((R, Sc), dtype=f32)
+    up = rng.random((R, max(Sf, 1)), dtype=f32)
+    hp = HotPath(n_coarse=Sc, n_fine=Sf, near=2.0, far=6.0, white_bkgd=True, device=dev)
+    sdc = {k: v.cpu() for k, v in hp.state_dict(0).items()}
+    sdf = {k: v.cpu() for k, v in hp.state_dict(1).items()} if Sf else None
+    cu = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    occ, wreg = (0.5, 2.0, "linear"), (mode, 1e-4)
+    args = (cu(o), cu(d), cu(gt), cu(us), cu(up) if Sf else None)
+    hp.train_step(*args, lr=5e-4, apply_update=False)
+    g_plain = hp.grads.clone()
+    hp.train_step(*args, lr=5e-4, apply_update=False, occ_reg=occ, weight_reg=wreg)
+    g_occ = hp.grads.clone()
+    clone = lambda sd: None if sd is None else {k: v.clone() for k, v in sd.items()}  # noqa: E731
+    _, _, ref_plain = orender.train_step(clone(sdc), clone(sdf), dict(step=0, m={}, v={}), o, d, gt, 2.0, 6.0,
+                                         Sc, Sf, us, up, 5e-4, True)
+    _, _, ref_g = orender.train_step(clone(sdc), clone(sdf), dict(step=0, m={}, v={}), o, d, gt, 2.0, 6.0,
+                                     Sc, Sf, us, up, 5e-4, True, occ_reg=occ)
+    # (1) the occlusion term's gradient contribution, isolated: (g_occ - g_plain) vs the oracle's
+    tag = "f." if Sf else "c."
+    net = 1 if Sf else 0
+    for (off, n), name in zip(hp.layout, hp.names):
+        if name.startswith(("connection", "branch", "rgb")):
+            continue  # sigma does not depend on the view branch (connection -> branch -> rgb)
+        ours = (g_occ - g_plain)[net * hp.n_net + off: net * hp.n_net + off + n].cpu().double()
+        ref = (ref_g[tag + name] - ref_plain[tag + name]).reshape(-1).double()
+        rel = ((ours - ref).norm() / ref.norm().clamp_min(1e-12)).item()
+        assert rel < 2e-2, (name, rel)
+    occ_ref = oreg_dense_value(sdf if Sf else sdc, sdc, o, d, Sc, Sf, us, up, occ)
+    assert abs(hp.occ_sum.item() / R - occ_ref) < 2e-3 * max(1.0, abs(occ_ref))
+    # (2) parameters after one regularised update vs the oracle's Adam on the regularised loss
+    sdc2 = {k: v.cpu() for k, v in hp.state_dict(0).items()}
+    sdf2 = {k: v.cpu() for k, v in hp.state_dict(1).items()} if Sf else None
+    orender.train_step(sdc2, sdf2, dict(step=0, m={}, v={}), o, d, gt, 2.0, 6.0, Sc, Sf, us, up, 5e-4, True,
+                       occ_reg=occ, weight_reg=wreg)
+    hp.train_step(*args, lr=5e-4, occ_reg=occ, weight_reg=wreg)
+    for net_i, sd in ((0, sdc2), (1, sdf2)):
+        if sd is None:
+            continue
+        ours = hp.state_dict(net_i)
+        for k in sd:
+            _check_adam_step(ours[k].cpu(), sd[k], 5e-4, k)
+
+
+def oreg_dense_value(sd_out, sdc, o, d, Sc, Sf, us, up, occ):
+    from oracle import regularizers as oreg
+    with torch.no_grad():
+        out = orender.render_rays_hier(sdc, sd_out, o, d, 2.0, 6.0, Sc, Sf, us, up if Sf else None, white_bkgd=True)
+        return oreg.occlusion_reg_dense(out["raw"][..., 3], out["t_starts"], out["t_ends"], *occ).item()

@@ -1,5 +1,6 @@
 """CPU tests: the oracle against the reference-generated golden fixtures and
 closed-form known answers."""
+import os
 import pytest
 import numpy as np
 import torch
@@ -326,3 +327,63 @@ def test_scheduler_mirror_matches_reference_values(golden):
     assert opt.param_groups[0]["lr"] == 3e-4
     with pytest.raises(ValueError):
         Constant(opt, 10, -1.0)
+
+
+# ------------------------------------------------------------------ in-step regularisers (f2)
+def test_regularizers_match_reference(golden):
+    """oracle/regularizers.py vs the reference's own core.loss.OcclusionRegularizer and the
+    weight-penalty loop of src/run-nerf.py:266-279 (fixture: oracle/gen_golden_reg.py)"""
+    from oracle import regularizers as oreg, mlp as omlp
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_reg.npz"))
+    ri, t = torch.from_numpy(g["occ_ray_idx"]), torch.from_numpy(g["occ_t"])
+    for func in ("linear", "exp"):
+        a, b = (float(x) for x in g[f"occ_{func}_ab"])
+        sig = torch.from_numpy(g["occ_sigma"]).requires_grad_(True)
+        val = oreg.occlusion_reg(sig, t, ri, a, b, func)
+        (gs,) = torch.autograd.grad(val, sig)
+        np.testing.assert_allclose(val.item(), g[f"occ_{func}_value"], rtol=1e-6)
+        np.testing.assert_allclose(gs.numpy(), g[f"occ_{func}_dsigma"], rtol=1e-6, atol=1e-8)
+    e = torch.from_numpy(g["occ_dense_edges"])
+    sg = torch.from_numpy(g["occ_dense_sigma"]).requires_grad_(True)
+    val = oreg.occlusion_reg_dense(sg, e[:, :-1], e[:, 1:], 0.5, 2.0, "linear")
+    (gs,) = torch.autograd.grad(val, sg)
+    np.testing.assert_allclose(val.item(), g["occ_dense_value"], rtol=1e-6)
+    np.testing.assert_allclose(gs.numpy(), g["occ_dense_dsigma"], rtol=1e-6, atol=1e-8)
+    # the survey's pinned known answer (SURVEY.md §8c)
+    v = oreg.occlusion_reg(torch.tensor([1., 1, 1, 2, 2]), torch.tensor([1., 2, 3, 1, 2]),
+                           torch.tensor([0, 0, 0, 2, 2]), 0.5, 2.0, "linear")
+    assert abs(v.item() - 4.0) < 1e-6
+    with pytest.raises(ValueError):
+        oreg.occlusion_weights(t, 1.0, 1.0, "cubic")
+
+    sd = omlp.init_state_dict(seed=42)
+    names = oreg.regularised_names([(k, tuple(v.shape)) for k, v in sd.items()])
+    assert names == list(g["wreg_covered"]) and len(names) == 10
+    assert "sigma.weight" not in names and "rgb.weight" not in names
+    for mode in ("l1", "l2"):
+        ps = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        val = oreg.weight_reg(ps, mode)
+        gl, gb = torch.autograd.grad(val, [ps["layers.5.weight"], ps["branch.weight"]])
+        np.testing.assert_allclose(val.item(), g[f"wreg_{mode}_value"], rtol=1e-6)
+        np.testing.assert_allclose(gl[:6, :40].numpy(), g[f"wreg_{mode}_grad_layers5"], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(gb[:6, :40].numpy(), g[f"wreg_{mode}_grad_branch"], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose([gl.abs().sum().item(), gb.abs().sum().item()],
+                                   g[f"wreg_{mode}_grad_abs_sums"], rtol=1e-5)
+
+
+def test_dropin_occlusion_regularizer_matches_reference():
+    """fsnerf_b200.core.loss (host-side mirror, torch ops only) vs the reference fixture"""
+    from fsnerf_b200.core.loss import OcclusionRegularizer
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_reg.npz"))
+    ri, t = torch.from_numpy(g["occ_ray_idx"]), torch.from_numpy(g["occ_t"])
+    for func in ("linear", "exp"):
+        a, b = (float(x) for x in g[f"occ_{func}_ab"])
+        sig = torch.from_numpy(g["occ_sigma"]).requires_grad_(True)
+        val = OcclusionRegularizer(a, b, func)(sig, t, ri)
+        (gs,) = torch.autograd.grad(val, sig)
+        np.testing.assert_allclose(val.item(), g[f"occ_{func}_value"], rtol=1e-6)
+        np.testing.assert_allclose(gs.numpy(), g[f"occ_{func}_dsigma"], rtol=1e-6, atol=1e-8)
+    with pytest.raises(AssertionError):
+        OcclusionRegularizer(-1.0, 1.0)
+    with pytest.raises(ValueError):
+        OcclusionRegularizer(1.0, 1.0, "cubic")(sig, t, ri)
