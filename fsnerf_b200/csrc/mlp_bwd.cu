@@ -626,6 +626,10 @@ extern "C" int fsnerf_mlp_backward(const fsnerf_net_cfg* cfg, const float* param
   if (variant < 0) {
     const char* e = getenv("FSNERF_BWD_VARIANT");
     variant = e ? atoi(e) : 2;
+    // the tensor-memory dgrad reads the 1-bit ReLU masks that only the second-generation
+    // forward writes into the stash
+    const char* f = getenv("FSNERF_FWD_VARIANT");
+    if (f && atoi(f) != 2) variant = 1;
   }
   if (variant == 2) {
     rc = mlp_dgrad_v2(P, packed, n_samples, stash, out, d_out, grads, workspace, stream);

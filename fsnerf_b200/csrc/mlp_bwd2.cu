@@ -1,8 +1,9 @@
 // Kernel (3) backward, second generation dgrad: the fused d(pre-activation) chain of the
 // NeRF MLP with the gradients resident in TENSOR MEMORY (the loss.backward() edge of
 // src/run-nerf.py:282 through src/core/models.py:111-143).  Same skeleton as mlp_fwd2.cu:
-//   warps 0..7   epilogue: TMEM -> regs -> (+ sigma-head term) -> ReLU mask from the forward
-//                stash -> bf16x2 written back IN PLACE as the next step's A operand; every
+//   warps 0..7   epilogue: TMEM -> regs (loads pipelined one chunk ahead) -> (+ sigma-head
+//                term) -> 1-bit ReLU mask written by the forward (32 B/sample/layer instead of
+//                re-reading the 512 B activations) -> bf16x2 written back IN PLACE as the next step's A operand; every
 //                finished chunk is handed to the MMA warps, staged through smem per 32-row
 //                slab and bulk-stored to the dstash image that wgrad streams back.
 //   warps 8..11  reducers: column sums of each staged slab = bias gradients (smem atomics)
@@ -53,7 +54,7 @@ __constant__ float c_smallB[kSmallFloats];
 
 struct StepB {
   int target;      // layer whose d(pre-activation) this step produces
-  int mask_off;    // stash offset of the target's forward output (ReLU mask), -1: none
+  int mask_off;    // stash offset of the 1-bit ReLU mask of the target's forward output, -1: none
   int add_sigma;   // add d(sigma) * w_sigma (target is the last hidden layer)
   int dstash_off;  // where the target's dpre image goes in the backward record
 };
@@ -73,21 +74,6 @@ struct ArgsB {
   uint8_t* dstash;
   int debug;  // tuning experiments only (FSNERF_DEBUG_FLAGS); results are wrong when non-zero
 };
-
-__device__ __forceinline__ uint4 ldg_u4(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
-// h = two post-ReLU bf16 (sign bits clear): 0xFFFF in each half whose value is non-zero,
-// i.e. relu'(h) as an AND mask for a packed bf16x2 gradient
-__device__ __forceinline__ uint32_t relu_mask2(uint32_t h) {
-  // h + 0x7FFF per half sets that half's top bit iff it is non-zero (no carry: h <= 0x7F80);
-  // PRMT with sign replication spreads bit 15 over bytes 0-1 and bit 31 over bytes 2-3
-  uint32_t r;
-  asm("prmt.b32 %0, %1, 0, 0xBB99;" : "=r"(r) : "r"(h + 0x7FFF7FFFu));
-  return r;
-}
-constexpr uint32_t kNoMask = 0x3F803F80u;  // "h" of an unmasked pair (bf16 1.0, 1.0)
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
 
 __global__ void __launch_bounds__(kThreadsB, 1)
 mlp_dgrad2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ PlanB plan,
@@ -234,30 +220,23 @@ mlp_dgrad2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant
         dz[2] = g4.z * o4.z * (1.0f - o4.z);
         dsig = g4.w;
       }
-      const uint32_t my_units = (uint32_t)(4 * half);
-      uint4 m[4];
       {
-        const uint8_t* hb = stash_tile + plan.branch_mask_off;
+        // ReLU masks are the 1-bit words the forward wrote (mlp_issue.cuh: relu_bits_*)
+        const uint8_t* bm = stash_tile + plan.branch_mask_off;
+        uint32_t bw = __ldg(reinterpret_cast<const uint32_t*>(bm + relu_bits_word_off(0, half, row)));
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           const int c0 = 64 * c + 32 * half;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) m[j] = ldg_u4(hb + c * kChunkBytes + sw128_off(row, my_units + j));
-          stage_wait();
-          if (half == 0 && plan.n_steps > 0 && plan.step[0].mask_off >= 0)
-            prefetch_l2(stash_tile + plan.step[0].mask_off + c * kChunkBytes + row * 128);
+          const uint32_t bw_next =
+              (c == 0) ? __ldg(reinterpret_cast<const uint32_t*>(bm + relu_bits_word_off(1, half, row))) : 0u;
           uint32_t w[16];
           const float* wr = heads + 256 + c0;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t mw[4] = {m[j].x, m[j].y, m[j].z, m[j].w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int i = 8 * j + 2 * q;
-              const float v0 = dz[0] * wr[i] + dz[1] * wr[128 + i] + dz[2] * wr[256 + i];
-              const float v1 = dz[0] * wr[i + 1] + dz[1] * wr[128 + i + 1] + dz[2] * wr[256 + i + 1];
-              w[4 * j + q] = pack_bf16x2(v0, v1) & relu_mask2(mw[q]);  // relu'(h): h == 0 <=> masked
-            }
+          for (int q = 0; q < 16; ++q) {
+            const int i = 2 * q;
+            const float v0 = dz[0] * wr[i] + dz[1] * wr[128 + i] + dz[2] * wr[256 + i];
+            const float v1 = dz[0] * wr[i + 1] + dz[1] * wr[128 + i + 1] + dz[2] * wr[256 + i + 1];
+            w[q] = pack_bf16x2(v0, v1) & relu_bits_mask2(bw, q);
           }
           // step 0 reads its A operand from region 1
           tmem_st16(tmem_lane + 256u + c0, w);
@@ -265,49 +244,38 @@ mlp_dgrad2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_a_ready + 8 * c);
+          stage_wait();
           stage_out(w);
+          bw = bw_next;
         }
       }
       // ---- chain
       for (int s = 0; s < plan.n_steps; ++s) {
         const StepB S = plan.step[s];
         const int r = s & 1;
-        const uint32_t region = tmem_lane + (uint32_t)r * 256u;
+        const uint32_t region = tmem_lane + (uint32_t)r * 256u + 32u * half;
         const bool last = (s == plan.n_steps - 1);
         const uint8_t* mimg = (S.mask_off >= 0 && !(args.debug & 1)) ? stash_tile + S.mask_off : nullptr;
-        const uint8_t* mnext = (!last && plan.step[s + 1].mask_off >= 0) ? stash_tile + plan.step[s + 1].mask_off : nullptr;
         const bool add_sigma = S.add_sigma != 0;
         // chunk 0's mask does not depend on the MMAs: fetch it before waiting on the accumulator
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          m[j] = mimg ? ldg_u4(mimg + sw128_off(row, my_units + j)) : make_uint4(kNoMask, kNoMask, kNoMask, kNoMask);
+        uint32_t mw = mimg ? __ldg(reinterpret_cast<const uint32_t*>(mimg + relu_bits_word_off(0, half, row))) : 0xFFFFFFFFu;
         if (threadIdx.x == 0 && args.trace && blockIdx.x == 0 && titer < 4) args.trace[(titer * 16 + s) * 8 + 3] = clock64();
         mbar_wait(bar_acc_full + 8 * r, acc_phase[r]);
         acc_phase[r] ^= 1;
         tc_fence_after();
         if (threadIdx.x == 0 && args.trace && blockIdx.x == 0 && titer < 4) args.trace[(titer * 16 + s) * 8 + 4] = clock64();
-#define FS_TD(k_) do { if (args.trace && threadIdx.x == 0 && blockIdx.x == 0 && titer == 1 && s < 4) args.trace[512 + ((s * 4 + c) * 8) + (k_)] = clock64(); } while (0)
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const int c0 = 64 * c + 32 * half;
-          uint32_t v[32];
-          FS_TD(0);
-          tmem_ld32(region + c0, v);
-          // next chunk's mask (one chunk ahead), next step's mask lines into L2
-          uint4 mn[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            mn[j] = (mimg && c < 3) ? ldg_u4(mimg + (c + 1) * kChunkBytes + sw128_off(row, my_units + j))
-                                    : make_uint4(kNoMask, kNoMask, kNoMask, kNoMask);
-          if (half == 0 && mnext) prefetch_l2(mnext + c * kChunkBytes + row * 128);
-          FS_TD(1);
-          stage_wait();
-          FS_TD(2);
-          tmem_ld_wait();
-          FS_TD(3);
+        // The accumulator loads are software-pipelined one chunk ahead through two register
+        // buffers: chunk c+1 is in flight from tensor memory while chunk c is converted, masked,
+        // written back as the next step's A operand and staged for the dstash.
+        auto chunk = [&](const int c, uint32_t (&v)[32], uint32_t (&vn)[32]) {
+          tmem_ld_wait();  // v = chunk c
+          if (c < 3) tmem_ld32(region + 64u * (c + 1), vn);
+          const uint32_t mwn = (mimg && c < 3)
+                                   ? __ldg(reinterpret_cast<const uint32_t*>(mimg + relu_bits_word_off(c + 1, half, row)))
+                                   : 0xFFFFFFFFu;
           uint32_t w[16];
-          const float* ws = heads + c0;
           if (add_sigma) {
+            const float* ws = heads + 64 * c + 32 * half;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 w4 = *reinterpret_cast<const float4*>(ws + 4 * i);
@@ -318,27 +286,25 @@ mlp_dgrad2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant
             }
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t mw[4] = {m[j].x, m[j].y, m[j].z, m[j].w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int i = 8 * j + 2 * q;
-              w[4 * j + q] = pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])) & relu_mask2(mw[q]);
-            }
-          }
-          FS_TD(4);
+          for (int q = 0; q < 16; ++q)
+            w[q] = pack_bf16x2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])) & relu_bits_mask2(mw, q);
           if (!last) {
-            tmem_st16(region + c0, w);
+            tmem_st16(region + 64u * c, w);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_a_ready + 8 * c);
           }
-          FS_TD(5);
+          stage_wait();
           stage_out(w);
-          FS_TD(6);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) m[j] = mn[j];
+          mw = mwn;
+        };
+        uint32_t va[32], vb[32];
+        tmem_ld32(region, va);
+#pragma unroll 1
+        for (int c = 0; c < 4; c += 2) {
+          chunk(c, va, vb);
+          chunk(c + 1, vb, va);
         }
         if (threadIdx.x == 0 && args.trace && blockIdx.x == 0 && titer < 4) args.trace[(titer * 16 + s) * 8 + 5] = clock64();
       }
@@ -373,7 +339,7 @@ int mlp_dgrad_v2(const MlpProgram& P, const void* packed, int64_t n_samples, con
   static IssueTable T;
   PL.n_steps = P.n_gemm - 1;
   PL.g_branch = P.n_gemm - 1;
-  PL.branch_mask_off = P.layer[P.n_gemm - 1].stash_off;
+  PL.branch_mask_off = P.layer[P.n_gemm - 1].mask_off;
   PL.branch_dstash_off = P.layer[P.n_gemm - 1].dstash_off;
   int j = 0;
   int n_cons[4] = {0, 0, 0, 0};
@@ -384,7 +350,7 @@ int mlp_dgrad_v2(const MlpProgram& P, const void* packed, int64_t n_samples, con
     const int src = P.n_gemm - 1 - s, tgt = src - 1;
     StepB& S = PL.step[s];
     S.target = tgt;
-    S.mask_off = (P.layer[tgt].epi == EPI_CONN) ? -1 : P.layer[tgt].stash_off;
+    S.mask_off = P.layer[tgt].mask_off;
     S.add_sigma = (P.layer[tgt].epi == EPI_RELU_SIGMA) ? 1 : 0;
     S.dstash_off = P.layer[tgt].dstash_off;
     const int nch = P.layer[src].bwd_n_chunks;

@@ -10,7 +10,8 @@
 //             W^T (rows = input features, K = output features).
 //  * stash    per 128-sample tile, the bf16 SWIZZLE_128B images of every GEMM
 //             input (exact byte image of the A operand in shared memory), so
-//             that the backward kernels can bulk-load them straight back.
+//             that the backward kernels can bulk-load them straight back, followed
+//             by the 1-bit ReLU masks of every layer output (4 KB per 256-wide layer).
 #pragma once
 #include <stdint.h>
 #include "../../include/fsnerf_b200.h"
@@ -53,6 +54,10 @@ struct GemmLayer {
   int bwd_n_halves;     // dgrad output width / 128 (2)
   int bwd_n_chunks;     // dgrad K chunks = N_out / 64
   int dstash_off;       // byte offset of d(pre-activation) image in a tile's backward record
+  // byte offset, in a tile's stash record, of the 1-bit ReLU mask of this layer's OUTPUT
+  // ([chunk][column half][128 rows] 32-bit words, see relu_bits_* in mlp_issue.cuh); -1: the
+  // layer has no ReLU.  dgrad reads these 32 B/sample/layer instead of the 512 B activations.
+  int mask_off;
 };
 
 struct MlpProgram {

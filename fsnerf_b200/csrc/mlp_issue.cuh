@@ -66,6 +66,26 @@ struct IssueBars {
   uint32_t ring;                    // smem address of the operand ring
 };
 
+// ------------------------------------------------------------------ 1-bit ReLU masks
+// One 32-bit word per (sample row, 32-column half of a 64-feature chunk).  Pair q of the half
+// (columns 2q, 2q+1, the bf16x2 word w[q] of the epilogues) owns bits 15-q and 31-q, so that
+// `word << q` puts them on the sign bits of bytes 1 and 3, where ONE PRMT with sign replication
+// expands them into the 0xFFFF / 0x0000 AND-mask of a packed bf16x2 gradient.
+// forward: fold pair q's non-zero flags into the word (h = two post-ReLU bf16, sign bits clear:
+// h + 0x7FFF per half sets that half's top bit iff it is non-zero; no carry since h <= 0x7FFF)
+__device__ __forceinline__ uint32_t relu_bits_fold(uint32_t word, uint32_t h, int q) {
+  return word | (((h + 0x7FFF7FFFu) & 0x80008000u) >> q);
+}
+// backward: AND-mask of pair q
+__device__ __forceinline__ uint32_t relu_bits_mask2(uint32_t word, int q) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, 0, 0xBB99;" : "=r"(r) : "r"(word << q));
+  return r;
+}
+__host__ __device__ __forceinline__ uint32_t relu_bits_word_off(int chunk, int half, int row) {
+  return (uint32_t)(((chunk * 2 + half) * kTileM + row) * 4);
+}
+
 // ------------------------------------------------------------------ weight producers
 // Producer `me` of kProdWarps streams every kProdWarps-th stage: L2 -> smem, one bulk copy.
 template <int kStages>

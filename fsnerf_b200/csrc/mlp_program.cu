@@ -99,6 +99,14 @@ int build_program(const fsnerf_net_cfg* cfg, MlpProgram* P) {
   P->n_gemm = g;
   P->n_blocks_fwd = blk;
   P->n_params = off;
+  // 1-bit ReLU masks behind the operand images (existing offsets stay put): per layer
+  // [n_out/64 chunks][2 column halves][128 rows] x 4 B
+  for (int gi = 0; gi < g; ++gi) {
+    GemmLayer& L = P->layer[gi];
+    if (L.epi == EPI_CONN) { L.mask_off = -1; continue; }
+    L.mask_off = stash;
+    stash += (L.n_halves * 2) * 2 * kTileM * 4;
+  }
   P->stash_tile_bytes = stash;
   // dgrad (W^T) blocks, in backward consumption order: branch, conn, hidden n-1 .. 1
   for (int gi = P->n_gemm - 1; gi >= 1; --gi) {
