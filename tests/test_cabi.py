@@ -43,7 +43,7 @@ def test_host_side_layout_queries():
     assert ops.mlp_packed_bytes(cfg) == (73 + 68) * 16384 + 4864 * 4
     # per 128-sample tile: 640 KB of bf16 operand images + 34 KB of 1-bit ReLU masks (8 x 4 KB + 2 KB)
     assert ops.mlp_stash_bytes(cfg, 128) == 640 * 1024 + 34 * 1024
-    assert ops.mlp_stash_bytes(cfg, 129) == 2 * 640 * 1024
+    assert ops.mlp_stash_bytes(cfg, 129) == 2 * (640 + 34) * 1024
     bad = ops.make_cfg(d_hidden=128)
     from fsnerf_b200._lib import FsnerfError
     with pytest.raises(FsnerfError, match="d_hidden must be 256"):
