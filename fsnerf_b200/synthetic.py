@@ -133,3 +133,32 @@ def make_llff_views(n_views, H, W, seed=42):
         poses.append(pose)
         imgs.append(rgb)
     return np.stack(poses).astype(f32), np.stack(imgs).astype(f32), focal
+
+
+def write_llff_scene(root, scene="synth", n_views=9, H=24, W=32, seed=42):
+    """Write ``<root>/<scene>/poses_bounds.npy`` + ``images_8/*.png`` in the LLFF layout read by the
+    reference's Splitter (/root/reference/src/nerfdata/utils/splitter.py:174-231): per view a 3x5
+    camera-to-world in LLFF axes (down, right, back | position | H, W, focal at FULL resolution,
+    i.e. 8x the images_8 frames) followed by the near/far depth bounds.  Forward-facing cameras
+    with small random rotations around (0, 0, RADIUS)."""
+    from PIL import Image
+    rng = np.random.default_rng(seed)
+    focal = focal_from_fov(W)
+    d = os.path.join(root, scene, "images_8")
+    os.makedirs(d, exist_ok=True)
+    rows = []
+    for v in range(n_views):
+        yaw, pitch = rng.uniform(-0.08, 0.08, 2)
+        ry = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])
+        rx = np.array([[1, 0, 0], [0, np.cos(pitch), -np.sin(pitch)], [0, np.sin(pitch), np.cos(pitch)]])
+        pose = np.eye(4)
+        pose[:3, :3] = ry @ rx
+        pose[:3, 3] = [rng.uniform(-0.6, 0.6), rng.uniform(-0.4, 0.4), RADIUS + rng.uniform(-0.1, 0.1)]
+        ro, rd = camera_rays(pose.astype(f32), H, W, focal)
+        rgb, _ = trace(ro, rd, True)
+        Image.fromarray((255 * np.clip(rgb, 0, 1)).astype(np.uint8), "RGB").save(os.path.join(d, f"img_{v:03d}.png"))
+        m = np.concatenate([-pose[:3, 1:2], pose[:3, 0:1], pose[:3, 2:3], pose[:3, 3:4],
+                            np.array([[8.0 * H], [8.0 * W], [8.0 * focal]])], 1)  # (down, right, back | t | hwf)
+        rows.append(np.concatenate([m.reshape(-1), [RADIUS - 1.6 + 0.05 * v, RADIUS + 1.6]]))
+    np.save(os.path.join(root, scene, "poses_bounds.npy"), np.stack(rows).astype(np.float64))
+    return os.path.join(root, scene)
