@@ -303,3 +303,52 @@ def oreg_dense_value(sd_out, sdc, o, d, Sc, Sf, us, up, occ):
     with torch.no_grad():
         out = orender.render_rays_hier(sdc, sd_out, o, d, 2.0, 6.0, Sc, Sf, us, up if Sf else None, white_bkgd=True)
         return oreg.occlusion_reg_dense(out["raw"][..., 3], out["t_starts"], out["t_ends"], *occ).item()
+
+
+@pytest.mark.gpu
+def test_c3_llff_ndc_freqmask_train_step(dev):
+    """BASELINE.json configs[2]: few-shot 3-view forward-facing scene, NDC rays (near plane 1.0,
+    samples in [0,1]) and the FreeNeRF annealed frequency mask — the fused step vs the oracle
+    on identical rays / uniforms / masks; then the mask schedule expiring (mask == ones)."""
+    from fsnerf_b200 import ops, synthetic as syn
+    from fsnerf_b200.engine import HotPath
+    from oracle import rays as orays, encoding as oenc
+    H, W, R, Sc, Sf = 36, 48, 512, 64, 64
+    poses, imgs, focal = syn.make_llff_views(3, H, W, seed=42)
+    rng = np.random.default_rng(11)
+    ids = rng.permutation(3 * H * W)[:R].astype(np.int64)
+    o_ref, d_ref = orays.rays_from_pixel_ids(poses, (H, W, focal), ids, ndc=True, ndc_near=1.0)
+    gt = imgs.reshape(-1, 3)[ids]
+    us, up = rng.random((R, Sc), dtype=f32), rng.random((R, Sf), dtype=f32)
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    # rays come from the kernel itself (a1 + a2 + a12 fused), pixel bookkeeping bit-exact
+    o, d, gt_k = ops.gen_rays(cu(poses), H, W, focal, pixel_ids=cu(ids), images=cu(imgs), ndc=True, ndc_near=1.0)
+    assert torch.equal(gt_k.cpu(), torch.from_numpy(gt))
+    np.testing.assert_allclose(o.cpu().numpy(), o_ref, atol=2e-6)
+    np.testing.assert_allclose(d.cpu().numpy(), d_ref, atol=2e-6)
+    hp = HotPath(n_coarse=Sc, n_fine=Sf, near=0.0, far=1.0, white_bkgd=True, device=dev)
+    step, reg_steps = 300, 900  # T_reg = 0.9 * n_iters with n_iters = 1000
+    hp.set_freq_mask(step, reg_steps)
+    mp, md = oenc.freq_mask(63, step, reg_steps), oenc.freq_mask(27, step, reg_steps)
+    assert torch.equal(hp.mask_pos.cpu(), torch.from_numpy(mp)) and torch.equal(hp.mask_dir.cpu(), torch.from_numpy(md))
+    assert 0 < mp.sum() < 63
+    sdc = {k: v.cpu() for k, v in hp.state_dict(0).items()}
+    sdf = {k: v.cpu() for k, v in hp.state_dict(1).items()}
+    ls = hp.train_step(o, d, gt_k, cu(us), cu(up), lr=5e-4, apply_update=False)
+    ref_loss, _, ref_g = orender.train_step(sdc, sdf, dict(step=0, m={}, v={}), o.cpu().numpy(), d.cpu().numpy(), gt,
+                                            0.0, 1.0, Sc, Sf, us, up, 5e-4, True, mask_pos=mp, mask_dir=md)
+    assert abs((ls[0].item() + ls[1].item()) / (3 * R) - ref_loss) < 2e-4
+    rels = {}
+    for net, tag in ((0, "c."), (1, "f.")):
+        flat = hp.grads[net * hp.n_net:(net + 1) * hp.n_net].cpu()
+        for (off, n), name in zip(hp.layout, hp.names):
+            g_ref = ref_g[tag + name].reshape(-1).double()
+            rels[tag + name] = ((flat[off:off + n].double() - g_ref).norm() / g_ref.norm().clamp_min(1e-12)).item()
+    # masked-out encoding channels carry exactly zero gradient into layers.0 / layers.5 / branch
+    lay = dict(zip(hp.names, hp.layout))
+    w0 = hp.grads[lay["layers.0.weight"][0]:lay["layers.0.weight"][0] + lay["layers.0.weight"][1]].view(256, 63)
+    assert float(w0[:, mp == 0].abs().max()) == 0.0 and float(w0[:, mp == 1].abs().max()) > 0.0
+    print("C3 grad rel err:", {k: round(v, 4) for k, v in rels.items()})
+    _check_grad_bar(rels, hp.grads.cpu(), hp, ref_g)
+    hp.set_freq_mask(reg_steps, reg_steps)
+    assert hp.mask_pos is None and hp.mask_dir is None
