@@ -82,6 +82,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// For warps that are NOT on the critical path (weight producers, store warps, encoders): back
+// off between polls so that the spin loop does not take issue slots from the epilogue and
+// MMA-issuer warps sharing the scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(128);
+    if (++spins > (1u << 22)) {
+      printf("fsnerf: mbarrier timeout blk %d thr %d bar %u parity %u\n", blockIdx.x, threadIdx.x,
+             bar, parity);
+      __trap();
+    }
+  }
+}
+
 // Same, for a warp that must stay provably CONVERGED (the MMA issuer): the loop exit is a
 // warp vote, so the compiler's divergence analysis keeps everything downstream uniform
 // (operands of the tcgen05 instructions then live in uniform registers).
@@ -94,6 +109,15 @@ __device__ __forceinline__ void mbar_wait_converged(uint32_t bar, uint32_t parit
       __trap();
     }
   }
+}
+
+// ---------------------------------------------------------------- register re-split per role
+// (warpgroup granularity: all four warps of an aligned group must execute the same one)
+template <int kRegs> __device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+template <int kRegs> __device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
 }
 
 // ---------------------------------------------------------------- proxies / fences

@@ -148,7 +148,7 @@ mlp_dgrad2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant
         for (int c = 0; c < nchunk; ++c, ++n_staged) {
           const uint32_t b = n_staged % kStageBufsB;
           const uint32_t buf = stage_base + b * kSlabBytesB;
-          mbar_wait(bar_slab_full + 8 * (quarter * kStageBufsB + b), (n_staged / kStageBufsB) & 1);
+          mbar_wait_relaxed(bar_slab_full + 8 * (quarter * kStageBufsB + b), (n_staged / kStageBufsB) & 1);
           if (!(args.debug & 4)) {
             // coalesced copy with plain loads/stores (512 B per warp instruction): the epilogue
             // then needs no generic->async proxy fence (a MEMBAR.ALL.CTA per chunk) to hand over

@@ -199,7 +199,7 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
         if (lane == 0) bulk_wait_read0();
         __syncwarp();
       }
-      mbar_wait(bar_pos_empty, (titer & 1) ^ 1);
+      mbar_wait_relaxed(bar_pos_empty, (titer & 1) ^ 1);
       encode_row(pos, prog.n_freqs_pos, prog.freq_pos, prog.pow2_freqs != 0, args.mask_pos,
                  sbase + S::aux_pos, row);
       fence_proxy_async_smem();
@@ -213,7 +213,7 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
         }
       }
       if (!args.density_only) {
-        mbar_wait(bar_dir_empty, (titer & 1) ^ 1);
+        mbar_wait_relaxed(bar_dir_empty, (titer & 1) ^ 1);
         encode_row(dir, prog.n_freqs_dir, prog.freq_dir, prog.pow2_freqs != 0, args.mask_dir,
                    sbase + S::aux_dir, row);
         fence_proxy_async_smem();

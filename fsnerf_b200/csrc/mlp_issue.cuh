@@ -96,7 +96,7 @@ __device__ __forceinline__ void producer_loop(const IssueTable& tab, const Issue
     for (int j = 0; j < tab.n; ++j, ++cnt) {
       if ((int)(cnt % kProdWarps) != me) continue;
       const uint32_t stage = cnt % kStages, phase = (cnt / kStages) & 1;
-      mbar_wait(B.w_empty + 8 * stage, phase ^ 1);
+      mbar_wait_relaxed(B.w_empty + 8 * stage, phase ^ 1);
       if (lane == 0) {
         const uint32_t bytes = tab.rec[j].w_bytes;
         mbar_arrive_expect_tx(B.w_full + 8 * stage, bytes);
