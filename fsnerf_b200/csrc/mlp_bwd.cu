@@ -300,8 +300,8 @@ mlp_dgrad_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant_
 }
 
 // =========================================================================== wgrad
-constexpr int kWStages = 6;
-constexpr int kSlabRows = 32;                     // samples per stage
+constexpr int kWStages = 3;
+constexpr int kSlabRows = 64;                     // samples per stage
 constexpr int kSlabBytes = kSlabRows * 128;       // 4 KB per 64-feature chunk
 constexpr int kWStageBytes = 8 * kSlabBytes;      // A: 4 chunks, B: 4 chunks
 constexpr int kWSmemBars = kWStages * kWStageBytes;
@@ -345,7 +345,7 @@ mlp_wgrad_kernel(const __grid_constant__ WgradPlan plan, const __grid_constant__
   if ((sbase & 1023u) != 0) __trap();
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWStages; ++s) {
-      mbar_init(bar_full + 8 * s, 4);   // four producer warps
+      mbar_init(bar_full + 8 * s, 8);   // eight issuing threads (two lanes of each of the four producer warps)
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_acc_full, 1);
@@ -364,9 +364,10 @@ mlp_wgrad_kernel(const __grid_constant__ WgradPlan plan, const __grid_constant__
   if (t1 > t0) {
     if (warp >= 2) {
       // four producer warps (the epilogue warps, idle during the main loop): bulk copies issued
-      // by one thread do not overlap (tools/l2_bench.cu), so each stage's 4 KB slab copies are
-      // spread over four issuing threads, each arming the stage barrier for its own bytes
-      const int pw = warp - 2;
+      // by one thread do not overlap (tools/l2_bench.cu), so each stage's slab copies (8 KB
+      // each: 64 rows of one chunk image) are spread over eight issuing threads, each arming
+      // the stage barrier for its own bytes
+      const int pw = (warp - 2) * 2 + lane;  // issuing thread index (lanes 0 and 1 issue)
       const int n_cp = J.a_chunks + J.b_chunks;
       uint32_t cnt = 0;
       for (int64_t tile = t0; tile < t1; ++tile) {
@@ -375,12 +376,12 @@ mlp_wgrad_kernel(const __grid_constant__ WgradPlan plan, const __grid_constant__
         for (int slab = 0; slab < kTileM / kSlabRows; ++slab, ++cnt) {
           const uint32_t stage = cnt % kWStages, phase = (cnt / kWStages) & 1;
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          if (lane == 0) {
+          if (lane < 2) {
             const uint32_t sa = sbase + stage * kWStageBytes, sb = sa + 4 * kSlabBytes;
             int mine = 0;
-            for (int c = pw; c < n_cp; c += 4) ++mine;
+            for (int c = pw; c < n_cp; c += 8) ++mine;
             mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)mine * kSlabBytes);
-            for (int c = pw; c < n_cp; c += 4) {
+            for (int c = pw; c < n_cp; c += 8) {
               if (c < J.a_chunks)
                 bulk_g2s(sa + c * kSlabBytes, a_img + c * kChunkBytes + slab * kSlabBytes, kSlabBytes,
                          bar_full + 8 * stage);
