@@ -376,8 +376,17 @@ def main():
     dom_ms_per_step = prof[dom][0] / K
     achieved = flops[dom] / (dom_ms_per_step / 1e3) / 1e12
     traffic, traffic_src = ncu_traffic(dom)
+    # the MLP kernels of the training step also move a lot of HBM (activation stash):
+    # DRAM bytes of the committed ncu capture / the live kernel time = how close each is to the HBM roof
+    dram = {}
+    for k in flops:
+        tb, _ = ncu_traffic(k)
+        if tb is not None and k in prof:
+            gbs = tb * (prof[k][1] / K) / (prof[k][0] / K / 1e3) / 1e9
+            dram[k] = {"gbs": gbs, "frac_of_hbm_peak": gbs / pk["hbm"]}
     roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": pk["tf_sus"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tf_sus"], "traffic": traffic, "traffic_source": traffic_src,
+                "dram_from_traffic": dram,
                 "peak_source": pk["src"] + " (sustained bf16)",
                 "launches_per_step": prof[dom][1] / K, "ms_per_step": dom_ms_per_step,
                 "kernel_ms_per_step": {k: v[0] / K for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
