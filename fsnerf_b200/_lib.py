@@ -38,6 +38,11 @@ SIGNATURES = {
     "fsnerf_composite_backward": (_i, [_l, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
     "fsnerf_composite_backward_occ": (_i, [_l, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p,
                                           _i, _f, _f, _f, _p, _p]),
+    "fsnerf_occgrid_march": (_i, [_l, _p, _p, _p, _f, _f, _f, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "fsnerf_composite_packed_forward": (_i, [_l, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "fsnerf_composite_packed_backward": (_i, [_l, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "fsnerf_occgrid_update": (_i, [_l, _p, _p, _f, _p, _p, _p]),
+    "fsnerf_occgrid_binarize": (_i, [_l, _p, _f, _p, _p]),
     "fsnerf_mlp_param_count": (_l, [C.POINTER(NetCfg)]),
     "fsnerf_mlp_param_layout": (_i, [C.POINTER(NetCfg), C.POINTER(_l), C.POINTER(_l), _i]),
     "fsnerf_mlp_packed_bytes": (_l, [C.POINTER(NetCfg)]),

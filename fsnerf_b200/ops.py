@@ -143,6 +143,79 @@ def composite_backward(raw, t_starts, t_ends, d_rgb, d_opacity=None, d_depth=Non
     return d_raw, d_bkgd
 
 
+# ---------------------------------------------- occupancy grid + packed compositing
+def occgrid_march(rays_o, rays_d, binaries, aabbs, step, near=0.0, far=1e10, near_planes=None):
+    """-> (ray_indices int64 [N], t_starts [N], t_ends [N], offsets int64 [R+1]); two launches of
+    the marching kernel (count, fill) around one exclusive scan of the per-ray counts."""
+    rays_o, rays_d = _f32c(rays_o, "rays_o"), _f32c(rays_d, "rays_d")
+    aabbs = _f32c(aabbs, "aabbs").reshape(-1, 6)
+    levels, res = binaries.shape[0], binaries.shape[1]
+    if binaries.dtype != torch.uint8:
+        binaries = binaries.to(torch.uint8)
+    binaries = binaries.contiguous()
+    R, dev = rays_o.shape[0], rays_o.device
+    counts = torch.zeros(R, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    args = (R, ptr(rays_o), ptr(rays_d), ptr(_f32c(near_planes, "near_planes")), float(near), float(far),
+            float(step), ptr(aabbs), int(levels), int(res), ptr(binaries))
+    check(lib.fsnerf_occgrid_march(*args, None, ptr(counts), None, None, None, _stream()), "fsnerf_occgrid_march")
+    offsets = torch.zeros(R + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(counts, 0, out=offsets[1:])
+    N = int(offsets[-1].item())  # packed size: the one host read of the sampler, as in nerfacc
+    ri = torch.empty(N, dtype=torch.int64, device=dev)
+    ts, te = torch.empty(N, device=dev), torch.empty(N, device=dev)
+    if N > 0:
+        check(lib.fsnerf_occgrid_march(*args, ptr(offsets), None, ptr(ri), ptr(ts), ptr(te), _stream()),
+              "fsnerf_occgrid_march")
+    return ri, ts, te, offsets
+
+
+def offsets_from_ray_indices(ray_indices, n_rays):
+    """[R+1] int64 segment offsets of sorted packed ray indices"""
+    counts = torch.bincount(ray_indices, minlength=n_rays)
+    offsets = torch.zeros(n_rays + 1, dtype=torch.int64, device=ray_indices.device)
+    torch.cumsum(counts, 0, out=offsets[1:])
+    return offsets
+
+
+def composite_packed_forward(raw, t_starts, t_ends, offsets, bkgd=None):
+    """raw [N,4] -> rgb [R,3], opacity [R,1], depth [R,1], weights [N], trans [N], alphas [N]"""
+    raw, ts, te = _f32c(raw, "raw"), _f32c(t_starts, "t_starts"), _f32c(t_ends, "t_ends")
+    R, N, dev = offsets.numel() - 1, ts.numel(), raw.device
+    rgb, op, dp = torch.empty(R, 3, device=dev), torch.empty(R, 1, device=dev), torch.empty(R, 1, device=dev)
+    w, tr, al = torch.empty(N, device=dev), torch.empty(N, device=dev), torch.empty(N, device=dev)
+    check(_lib.load().fsnerf_composite_packed_forward(R, ptr(offsets), ptr(raw), ptr(ts), ptr(te),
+                                                      ptr(_f32c(bkgd, "bkgd")), ptr(rgb), ptr(op), ptr(dp), ptr(w),
+                                                      ptr(tr), ptr(al), _stream()), "fsnerf_composite_packed_forward")
+    return rgb, op, dp, w, tr, al
+
+
+def composite_packed_backward(raw, t_starts, t_ends, offsets, trans, d_rgb, d_opacity=None, d_depth=None,
+                              d_weights=None, bkgd=None, want_d_bkgd=False):
+    raw, ts, te = _f32c(raw, "raw"), _f32c(t_starts, "t_starts"), _f32c(t_ends, "t_ends")
+    R = offsets.numel() - 1
+    d_raw = torch.empty_like(raw)
+    d_bkgd = torch.zeros(3, device=raw.device) if want_d_bkgd else None
+    check(_lib.load().fsnerf_composite_packed_backward(
+        R, ptr(offsets), ptr(raw), ptr(ts), ptr(te), ptr(_f32c(trans, "trans")), ptr(_f32c(bkgd, "bkgd")),
+        ptr(_f32c(d_rgb, "d_rgb")), ptr(_f32c(d_opacity, "d_opacity")), ptr(_f32c(d_depth, "d_depth")),
+        ptr(_f32c(d_weights, "d_weights")), ptr(d_raw), ptr(d_bkgd), _stream()), "fsnerf_composite_packed_backward")
+    return d_raw, d_bkgd
+
+
+def occgrid_update(occs, occ, cell_ids=None, decay=0.95):
+    """in place: occs[c] = max(decay*occs[c], max of the candidates occ[i] in cell c)"""
+    occ = _f32c(occ, "occ").reshape(-1)
+    ws = torch.empty_like(occ)
+    check(_lib.load().fsnerf_occgrid_update(occ.numel(), ptr(cell_ids), ptr(occ), float(decay), ptr(occs), ptr(ws),
+                                            _stream()), "fsnerf_occgrid_update")
+
+
+def occgrid_binarize(occs, threshold, binaries):
+    check(_lib.load().fsnerf_occgrid_binarize(occs.numel(), ptr(occs), float(threshold), ptr(binaries), _stream()),
+          "fsnerf_occgrid_binarize")
+
+
 # -------------------------------------------------------------------- MLP
 def make_cfg(n_layers=8, d_hidden=256, skip=(4,), n_freqs_pos=10, n_freqs_dir=4, log_space=True):
     mask = 0

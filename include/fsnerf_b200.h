@@ -101,6 +101,40 @@ int fsnerf_composite_backward_occ(int64_t n_rays, int n_samples, const float* ra
                                   float occ_a, float occ_b, float occ_scale, float* occ_loss_sum,
                                   void* stream);
 
+/* ---- occupancy-grid sampler + packed compositing -------- */
+/* Replaces nerfacc's OccGridEstimator.sampling as called at
+ * src/render/rendering.py:66-74 (ray/box slab test + fixed-step marching through
+ * binaries[levels][res][res][res], z fastest; aabbs [levels][6], level l encloses l-1).
+ * Interval k = [t_begin + k*step, +step), t_begin = max(near plane, box entry); kept iff
+ * its midpoint is before min(far, box exit) and in an occupied cell of the finest level
+ * containing it.  near_planes [n_rays] (per-ray, jittered when stratified) or NULL -> near.
+ * Count pass: offsets == NULL, writes counts[n_rays].  Fill pass: offsets = exclusive scan
+ * of counts; writes ray_indices (int64), t_starts, t_ends in ray-major packed order. */
+int fsnerf_occgrid_march(int64_t n_rays, const float* rays_o, const float* rays_d,
+                         const float* near_planes, float near, float far, float step,
+                         const float* aabbs, int levels, int res, const uint8_t* binaries,
+                         const int64_t* offsets, int32_t* counts, int64_t* ray_indices,
+                         float* t_starts, float* t_ends, void* stream);
+/* nerfacc.volrend.rendering (src/render/rendering.py:89-96) on packed samples: ray r owns
+ * [offsets[r], offsets[r+1]); raw [N,4] = (rgb, sigma).  Outputs rgb [R,3], opacity [R],
+ * depth [R], weights [N]; trans / alphas [N] optional (trans is what the backward reads). */
+int fsnerf_composite_packed_forward(int64_t n_rays, const int64_t* offsets, const float* raw,
+                                    const float* t_starts, const float* t_ends, const float* bkgd,
+                                    float* rgb, float* opacity, float* depth, float* weights,
+                                    float* trans, float* alphas, void* stream);
+int fsnerf_composite_packed_backward(int64_t n_rays, const int64_t* offsets, const float* raw,
+                                     const float* t_starts, const float* t_ends, const float* trans,
+                                     const float* bkgd, const float* d_rgb, const float* d_opacity,
+                                     const float* d_depth, const float* d_weights, float* d_raw,
+                                     float* d_bkgd, void* stream);
+/* OccGridEstimator.update_every_n_steps (src/run-nerf.py:288-295): occs[c] = max(decay*occs[c],
+ * max of the candidates occ[i] with cell_ids[i] == c) (cell_ids NULL: i == c); workspace n floats.
+ * binarize: binaries[c] = occs[c] > threshold. */
+int fsnerf_occgrid_update(int64_t n, const int64_t* cell_ids, const float* occ, float decay,
+                          float* occs, float* workspace, void* stream);
+int fsnerf_occgrid_binarize(int64_t n_cells, const float* occs, float threshold, uint8_t* binaries,
+                            void* stream);
+
 /* ---- (2)+(3) NeRF MLP -------------------------------------------------- */
 /* Architecture of core.models.NeRF (src/core/models.py:57-109). */
 typedef struct fsnerf_net_cfg {

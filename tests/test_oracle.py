@@ -387,3 +387,43 @@ def test_dropin_occlusion_regularizer_matches_reference():
         OcclusionRegularizer(-1.0, 1.0)
     with pytest.raises(ValueError):
         OcclusionRegularizer(1.0, 1.0, "cubic")(sig, t, ri)
+
+
+# ------------------------------------------------------------------ occupancy grid (f1)
+def test_occgrid_oracle_known_answers():
+    """closed-form checks of oracle/occgrid.py (the statement of semantics for csrc/occgrid.cu)"""
+    from oracle import occgrid as oocc
+    aabbs = oocc.level_aabbs([-1, -1, -1, 1, 1, 1], 2)
+    np.testing.assert_array_equal(aabbs, np.array([[-1, -1, -1, 1, 1, 1], [-2, -2, -2, 2, 2, 2]], np.float32))
+    binaries = np.zeros((1, 4, 4, 4), bool)
+    binaries[0, 2, 2, 1] = True                      # cell x,y in [0,.5), z in [-.5,0)
+    o = np.array([[0.25, 0.25, -3.0], [0.25, 0.25, -3.0], [5.0, 5.0, -3.0]], np.float32)
+    d = np.array([[0, 0, 1.0], [0, 0, 1.0], [0, 0, 1.0]], np.float32)
+    ri, ts, te = oocc.march(o, d, binaries, aabbs[:1], 0.125, near_planes=np.array([0, 0.0625, 0], np.float32))
+    # ray 0 enters at t=2: lattice 2 + k/8, midpoints inside z in [-.5,0) <=> t_mid in [2.5,3): k = 4..7
+    np.testing.assert_array_equal(ri, [0, 0, 0, 0, 1, 1, 1, 1])
+    np.testing.assert_allclose(ts[:4], [2.5, 2.625, 2.75, 2.875])
+    np.testing.assert_allclose(te - ts, 0.125)
+    # jitter below the entry distance has no effect (near plane = 0 + u*step < 2): same samples
+    np.testing.assert_array_equal(ts[4:], ts[:4])
+    # camera inside the box: the lattice starts at the (jittered) near plane
+    ri2, ts2, _ = oocc.march(np.array([[0.25, 0.25, -0.75]], np.float32), d[:1], binaries, aabbs[:1], 0.125,
+                             near_planes=np.array([0.0625], np.float32))
+    np.testing.assert_allclose(ts2, [0.1875, 0.3125, 0.4375, 0.5625])
+    # two levels: the point is looked up in the finest level that contains it
+    b2 = np.zeros((2, 4, 4, 4), bool)
+    b2[1] = True
+    ri3, ts3, _ = oocc.march(o[:1], d[:1], b2, aabbs, 0.5)
+    np.testing.assert_allclose(ts3, [1.0, 1.5, 4.0, 4.5])  # outer shell only: level 0 is empty
+    # visibility: trans = exp(-exclusive sum sigma*delta) >= eps
+    keep = oocc.visibility(np.full(6, 40.0, np.float32), np.arange(6, dtype=np.float32) * 0.1,
+                           np.arange(1, 7, dtype=np.float32) * 0.1, np.array([0, 0, 0, 0, 1, 1]), 1e-4)
+    np.testing.assert_array_equal(keep, [True, True, True, False, True, True])
+    # update + binarize
+    occs = oocc.update(np.array([0.0, 0.2, 0.0, 0.4], np.float32), np.array([0.1, 0.05, 0.3], np.float32),
+                       np.array([0, 1, 1]))
+    np.testing.assert_allclose(occs, [0.1, 0.3, 0.0, 0.4], rtol=1e-6)
+    b, thre = oocc.binarize(occs, 1e-2)
+    assert thre == 1e-2 and list(b) == [True, True, False, True]
+    b, thre = oocc.binarize(np.array([0.001, 0.003, 0.0, 0.0], np.float32), 1e-2)
+    assert abs(thre - 0.001) < 1e-9 and list(b) == [False, True, False, False]
