@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -291,6 +292,46 @@ def main():
     h2d = 3 * R_PER_GPU * 3 * 4
     d2h = 8
 
+    # ---- the reference's own train loop (src/run-nerf.py:232-285) on the drop-in modules: render_rays
+    #      through autograd, F.mse_loss, loss.backward(), torch.optim.Adam.  Reported beside the
+    #      fused engine so the cost of staying inside the reference's loop structure is visible.
+    dropin = None
+    if rank == 0 and not args.no_dropin:
+        import torch.nn.functional as Fnn
+        from fsnerf_b200.core.models import NeRF
+        from fsnerf_b200.render.rendering import HierarchicalEstimator, render_rays
+        kw = {"pos_fn": {"n_freqs": 10, "log_space": True}, "dir_fn": {"n_freqs": 4, "log_space": True}}
+        torch.manual_seed(42)
+        coarse, fine = NeRF(3, 3, 8, 256, [4], **kw).to(dev), NeRF(3, 3, 8, 256, [4], **kw).to(dev)
+        est = HierarchicalEstimator(near=NEAR, far=FAR, n_coarse=N_COARSE, n_fine=N_FINE, proposal_model=coarse)
+        opt = torch.optim.Adam(list(fine.parameters()) + list(coarse.parameters()), lr=5e-4)
+        fine.train(); coarse.train(); est.train()
+
+        def step_dropin(i):
+            ro, rd, gt = (b.to(dev, non_blocking=True) for b in host_batches[i])
+            (rgb, *_, extras), _, _ = render_rays(ro, rd, est, fine, train=True, white_bkgd=True, device=dev)
+            loss = Fnn.mse_loss(rgb, gt) + Fnn.mse_loss(extras["rgb_coarse"], gt)
+            loss.backward()
+            opt.step()
+            opt.zero_grad()
+            return loss
+        Kd = min(K, 10)
+        for i in range(W_):
+            step_dropin(i)
+        torch.cuda.synchronize()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for i in range(Kd):
+            last = step_dropin(W_ + i)
+        float(last)  # D2H read of the loss
+        d1.record()
+        torch.cuda.synchronize()
+        ms_d = d0.elapsed_time(d1) / Kd
+        dropin = {"value": R_PER_GPU / (ms_d / 1e3), "unit": "rays/s", "ms_per_step": ms_d, "steps": Kd,
+                  "what": "render_rays (autograd) + F.mse_loss + loss.backward() + torch.optim.Adam, "
+                          "host batches, one GPU"}
+        del coarse, fine, est, opt
+
     # ---- render Mrays/s (rank-local pixel slice of one 800x800 frame; no collective)
     render = None
     if not args.no_render:
@@ -403,6 +444,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e / Ke},
             "gpu_launches": launches, "roofline": roofline, "roofline_compositing": comp, "cpu_baseline": base, "render": render,
+            "dropin_loop": dropin,
             "clocks": sampler.summary(), "final_loss": final_loss,
             "mlp_model_flops_per_ray": (N_COARSE + N_COARSE + N_FINE) * F_TRAIN}
     print(json.dumps(line))
