@@ -323,7 +323,7 @@ def main():
         d0.record()
         for i in range(Kd):
             last = step_dropin(W_ + i)
-        float(last)  # D2H read of the loss
+        float(last.detach())  # D2H read of the loss
         d1.record()
         torch.cuda.synchronize()
         ms_d = d0.elapsed_time(d1) / Kd
