@@ -26,10 +26,20 @@ class PositionalEncoder(nn.Module):
         self.log_space = log_space
         self.d_output = d_input * (1 + 2 * n_freqs)
 
-    def forward(self, x):
-        raise FsnerfError(
-            "PositionalEncoder.forward: the B200 path never materialises the encoding "
-            "(it is fused into the first MLP layer's operand staging); call NeRF(x, dirs).")
+    def frequencies(self) -> Tensor:
+        """reference :31-34: 2^linspace(0, L-1, L) (log space) or linspace(1, 2^(L-1), L)"""
+        if self.log_space:
+            return 2.0 ** torch.linspace(0.0, self.n_freqs - 1, self.n_freqs)
+        return torch.linspace(2.0 ** 0.0, 2.0 ** (self.n_freqs - 1), self.n_freqs)
+
+    def forward(self, x, mask=None):
+        """[..., d_input] -> [..., d_output] on the device (standalone kernel ``fsnerf_encode``; inside
+        NeRF the same encoding is fused into the first layer's operand staging and never materialised).
+        Inference only, like every direct use in the reference."""
+        if not x.is_cuda:
+            raise FsnerfError("PositionalEncoder.forward: CUDA tensor required (no CPU path)")
+        out = ops.encode(x.reshape(-1, self.d_input), self.frequencies().to(x.device), mask)
+        return out.reshape(*x.shape[:-1], self.d_output)
 
 
 class _NeRFFunction(torch.autograd.Function):

@@ -247,6 +247,49 @@ extern "C" int fsnerf_to_ndc(const float* rays_o, const float* rays_d, int64_t n
   return fsnerf_check_launch("to_ndc");
 }
 
+// ---------------------------------------------------------------- standalone encoding
+// M.PositionalEncoder.forward (src/core/models.py:43-50) for callers that want the encoding
+// itself: out[p] = [x, sin(f0 x), cos(f0 x), ..., sin(f_{L-1} x), cos(f_{L-1} x)] (x mask).
+// Inside the MLP the encoding is never materialised (mlp_encode.cuh); this kernel is HBM
+// bound: 4 d in, 4 d (1 + 2L) out per point.  One thread per (point, frequency slot).
+namespace {
+__global__ void encode_kernel(int64_t n, int d_in, int n_freqs, const float* __restrict__ freqs,
+                              const float* __restrict__ mask, const float* __restrict__ x,
+                              float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int slots = 1 + n_freqs;
+  if (i >= n * slots) return;
+  const int64_t p = i / slots;
+  const int k = (int)(i - p * slots);  // 0: identity, 1 + j: frequency j
+  const int d_out = d_in * (1 + 2 * n_freqs);
+  float* o = out + p * d_out;
+  for (int a = 0; a < d_in; ++a) {
+    const float v = x[p * d_in + a];
+    if (k == 0) {
+      o[a] = mask ? v * mask[a] : v;
+    } else {
+      float sn, cs;
+      sincosf(v * freqs[k - 1], &sn, &cs);
+      const int c = d_in + 2 * d_in * (k - 1) + a;
+      o[c] = mask ? sn * mask[c] : sn;
+      o[c + d_in] = mask ? cs * mask[c + d_in] : cs;
+    }
+  }
+}
+}  // namespace
+
+extern "C" int fsnerf_encode(int64_t n_points, int d_input, int n_freqs, const float* freqs,
+                             const float* mask, const float* x, float* out, void* stream) {
+  if (n_points == 0) return FSNERF_OK;
+  FS_REQUIRE(x && out && (freqs || n_freqs == 0), "encode: null pointer");
+  FS_REQUIRE(d_input >= 1 && n_freqs >= 0 && n_freqs <= 64, "encode: bad sizes");
+  const int64_t total = n_points * (1 + n_freqs);
+  FsProfScope prof_("encode", stream);
+  encode_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n_points, d_input, n_freqs, freqs,
+                                                                                   mask, x, out);
+  return fsnerf_check_launch("encode");
+}
+
 extern "C" int fsnerf_sample_stratified(int64_t n_rays, int n_samples, float near, float far,
                                         const float* u, float* t_starts, float* t_ends,
                                         void* stream) {

@@ -143,6 +143,17 @@ def composite_backward(raw, t_starts, t_ends, d_rgb, d_opacity=None, d_depth=Non
     return d_raw, d_bkgd
 
 
+def encode(x, freqs, mask=None):
+    """standalone positional encoding: x [P,d] -> [P, d*(1+2L)] fp32 (reference channel order)"""
+    x = _f32c(x, "x")
+    P, d = x.shape
+    L = freqs.numel()
+    out = torch.empty(P, d * (1 + 2 * L), device=x.device)
+    check(_lib.load().fsnerf_encode(P, d, L, ptr(_f32c(freqs, "freqs")), ptr(_f32c(mask, "mask")), ptr(x), ptr(out),
+                                    _stream()), "fsnerf_encode")
+    return out
+
+
 # ---------------------------------------------- occupancy grid + packed compositing
 def occgrid_march(rays_o, rays_d, binaries, aabbs, step, near=0.0, far=1e10, near_planes=None):
     """-> (ray_indices int64 [N], t_starts [N], t_ends [N], offsets int64 [R+1]); two launches of

@@ -101,6 +101,14 @@ int fsnerf_composite_backward_occ(int64_t n_rays, int n_samples, const float* ra
                                   float occ_a, float occ_b, float occ_scale, float* occ_loss_sum,
                                   void* stream);
 
+/* ---- (2) standalone positional encoding ---------------------------------- */
+/* M.PositionalEncoder.forward (src/core/models.py:43-50): x [P,d_input] ->
+ * out [P, d_input*(1+2*n_freqs)] = [x, sin(f_0 x), cos(f_0 x), ...] fp32; freqs
+ * [n_freqs] device floats; mask [d_out] (FreeNeRF, Appendix B4) or NULL.  The MLP
+ * kernels fuse the same encoding into their first-layer operand staging and never call this. */
+int fsnerf_encode(int64_t n_points, int d_input, int n_freqs, const float* freqs, const float* mask,
+                  const float* x, float* out, void* stream);
+
 /* ---- occupancy-grid sampler + packed compositing -------- */
 /* Replaces nerfacc's OccGridEstimator.sampling as called at
  * src/render/rendering.py:66-74 (ray/box slab test + fixed-step marching through

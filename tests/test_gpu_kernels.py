@@ -367,3 +367,22 @@ def test_adam_with_weight_penalty(dev, mode):
         ours = _unflatten(cfg, p)
         for k in ref:
             assert (ours[k] - ref[k].detach().reshape(-1)).abs().max().item() < 2e-6, (k, step)
+
+
+@pytest.mark.gpu
+def test_standalone_positional_encoder(dev, golden):
+    """M.PositionalEncoder.forward as a standalone kernel vs the reference's own outputs"""
+    from fsnerf_b200.core.models import PositionalEncoder
+    g = golden("reference_mlp.npz")
+    x, d = torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["d"]).to(dev)
+    pe = PositionalEncoder(3, 10, True)
+    assert pe.d_output == 63
+    np.testing.assert_allclose(pe(x).cpu().numpy(), g["pe_pos"], atol=2e-6 * 512)  # |arg| up to 2^9: few-ulp sincos
+    np.testing.assert_allclose(PositionalEncoder(3, 4, True)(d).cpu().numpy(), g["pe_dir"], atol=4e-6)
+    np.testing.assert_allclose(PositionalEncoder(3, 4, False)(d).cpu().numpy(), g["pe_lin"], atol=4e-6)
+    pin = torch.tensor([[0.1, -0.2, 0.3]], device=dev)
+    np.testing.assert_allclose(pe(pin).cpu().numpy(), g["pe_pin"], atol=2e-5)
+    from oracle import encoding as oenc
+    m = torch.from_numpy(oenc.freq_mask(63, 300, 900)).to(dev)
+    np.testing.assert_allclose(pe(x, m).cpu().numpy(), g["pe_pos"] * m.cpu().numpy(), atol=2e-6 * 512)
+    assert pe(x[:0]).shape == (0, 63) and pe(x.reshape(2, -1, 3)).shape[:2] == (2, x.shape[0] // 2)
