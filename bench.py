@@ -34,6 +34,7 @@ N_COARSE, N_FINE = 64, 128
 NEAR, FAR = 2.0, 6.0
 F_FWD = 1_186_816      # FLOP per sample evaluation, forward
 F_TRAIN = 3_489_024    # forward + backward
+F_DENSITY = 982_528    # density-only forward (the coarse pass of a hierarchical RENDER skips the view branch)
 METRIC = "train_rays_per_s"
 
 
@@ -364,10 +365,11 @@ def main():
         fwd_ms, fwd_n = rprof.get("mlp_fwd", (0.0, 1))
         render = {"value": world * n_chunks * chunk / (ms_r / 1e3) / 1e6, "unit": "Mrays/s",
                   "chunk_rays": chunk, "chunks": n_chunks, "frame": f"{RH}x{RW}",
-                  "mlp_fwd_tflops": (n_chunks * chunk * (N_COARSE + N_COARSE + N_FINE) * F_FWD) / (fwd_ms / 1e3) / 1e12
-                  if fwd_ms > 0 else None,
-                  "mlp_fwd_frac_of_bf16_peak": ((n_chunks * chunk * (N_COARSE + N_COARSE + N_FINE) * F_FWD)
-                                                / (fwd_ms / 1e3) / 1e12 / pk["tf_sus"]) if fwd_ms > 0 else None}
+                  "mlp_fwd_tflops": (n_chunks * chunk * (N_COARSE * F_DENSITY + (N_COARSE + N_FINE) * F_FWD))
+                  / (fwd_ms / 1e3) / 1e12 if fwd_ms > 0 else None,
+                  "mlp_fwd_frac_of_bf16_peak": ((n_chunks * chunk * (N_COARSE * F_DENSITY + (N_COARSE + N_FINE) * F_FWD))
+                                                / (fwd_ms / 1e3) / 1e12 / pk["tf_sus"]) if fwd_ms > 0 else None,
+                  "flops_per_ray": N_COARSE * F_DENSITY + (N_COARSE + N_FINE) * F_FWD}
 
     # ---- compositing kernel at render scale (HBM roofline of kernel (4); SURVEY.md §7 "hard parts":
     #      at training sizes it is launch-latency bound and L2 resident)

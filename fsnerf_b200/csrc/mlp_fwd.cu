@@ -296,7 +296,7 @@ mlp_fwd_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ 
         }
         if (last && valid) {
           if (args.density_only) {
-            args.out[p] = sigma;
+            args.out[args.density_only == 2 ? 4 * p + 3 : p] = sigma;
           } else {
             float r3[3];
 #pragma unroll
@@ -331,6 +331,7 @@ extern "C" int fsnerf_mlp_forward(const fsnerf_net_cfg* cfg, const float* params
   int rc = build_program(cfg, &P);
   if (rc != FSNERF_OK) return rc;
   FS_REQUIRE(n_samples >= 0, "mlp_forward: negative n_samples");
+  FS_REQUIRE(density_only >= 0 && density_only <= 2, "mlp_forward: density_only must be 0, 1 or 2");
   if (n_samples == 0) return FSNERF_OK;
   FS_REQUIRE(params && packed && out, "mlp_forward: null pointer");
   if (x) {

@@ -346,7 +346,8 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
           if (half == 1) exch[row].w = sig_part;
           named_bar_sync(1 + quarter, 64);
           if (half == 0) sigma = sig_part + exch[row].w + c_small2[kSmallSigmaB];
-          if (last && half == 0 && valid) args.out[p] = sigma;  // density_only
+          // density_only: 1 -> out [P]; 2 -> the sigma slot of a [P,4] (rgb, sigma) buffer
+          if (last && half == 0 && valid) args.out[args.density_only == 2 ? 4 * p + 3 : p] = sigma;
         } else if (epi == EPI_BRANCH) {
           if (half == 1) {
             exch[row].x = part[0]; exch[row].y = part[1]; exch[row].z = part[2];

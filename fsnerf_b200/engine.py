@@ -105,6 +105,14 @@ class HotPath:
             self._buf[key] = b
         return b
 
+    def _zeros4(self, key, n):
+        """cached zero-initialised [n,4] buffer (rgb slots stay 0: only sigma is written)"""
+        b = self._buf.get(key)
+        if b is None or b.shape[0] != n:
+            b = torch.zeros(n, 4, device=self.device)
+            self._buf[key] = b
+        return b
+
     def _pack(self):
         if not self._packed_fresh:
             for i, pk in enumerate(self.packed):
@@ -118,9 +126,13 @@ class HotPath:
         self._pack()
         ts_c, te_c = ops.sample_stratified(R, self.n_coarse, self.near, self.far, u_strat, device=self.device)
         st_c = self._bytes("stash_c", ops.mlp_stash_bytes(cfg, R * self.n_coarse)) if train else None
+        # rendering a hierarchical model needs only the WEIGHTS of the coarse pass: skip its view
+        # branch (17 % of its FLOPs) and write sigma straight into the compositor's (rgb, sigma) layout
+        sigma_only = (not train) and self.hier
         raw_c = ops.mlp_forward(cfg, self.net_params(0), self.packed[0], rays_o=rays_o, rays_d=rays_d,
                                 t_starts=ts_c, t_ends=te_c, mask_pos=self.mask_pos, mask_dir=self.mask_dir,
-                                stash=st_c)
+                                stash=st_c, density_only=2 if sigma_only else 0,
+                                out=self._zeros4("raw_c", R * self.n_coarse) if sigma_only else None)
         rgb_c, op_c, dp_c, w_c, _, _ = ops.composite_forward(raw_c.view(R, self.n_coarse, 4), ts_c, te_c,
                                                              bkgd=self.bkgd)
         self.launches += 3

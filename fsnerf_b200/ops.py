@@ -310,7 +310,10 @@ def mlp_forward(cfg, params, packed, *, rays_o=None, rays_d=None, t_starts=None,
         t_starts, t_ends = _f32c(t_starts, "t_starts"), _f32c(t_ends, "t_ends")
         P, S = t_starts.numel(), t_starts.shape[-1]
     if out is None:
-        out = torch.empty((P,) if density_only else (P, 4), device=params.device)
+        # density_only: False/0 full, True/1 sigma [P], 2 sigma into the .w slot of a zeroed [P,4]
+        out = (torch.empty(P, device=params.device) if int(density_only) == 1 else
+               torch.zeros(P, 4, device=params.device) if int(density_only) == 2 else
+               torch.empty(P, 4, device=params.device))
     check(_lib.load().fsnerf_mlp_forward(
         C.byref(cfg), ptr(params), ptr(packed), P, S, ptr(rays_o), ptr(rays_d), ptr(t_starts),
         ptr(t_ends), ptr(x), ptr(dirs), ptr(_f32c(mask_pos, "mask_pos")),

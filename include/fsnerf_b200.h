@@ -177,8 +177,10 @@ int fsnerf_mlp_pack(const fsnerf_net_cfg* cfg, const float* params, void* packed
  * p / samples_per_ray, position o + d*(t_starts[p]+t_ends[p])/2, view dir d.
  * If x != NULL the positions (and dirs, if given) are read from x/dirs [P,3]
  * instead (plain model(x, dirs) call).  mask_pos [3(1+2Lp)] / mask_dir
- * [3(1+2Ld)] or NULL (FreeNeRF mask, App. B4).  density_only: out is [P]
- * sigma (model(x) form) else [P,4] = (rgb, sigma).  stash: NULL for inference,
+ * [3(1+2Ld)] or NULL (FreeNeRF mask, App. B4).  density_only: 0 -> out is [P,4] =
+ * (rgb, sigma); 1 -> out is [P] sigma (model(x) form, the view branch is skipped);
+ * 2 -> as 1 but sigma is written to the .w slot of a [P,4] buffer (rgb untouched), so a
+ * proposal / coarse pass whose colours are not needed feeds the compositor directly.  stash: NULL for inference,
  * else fsnerf_mlp_stash_bytes() bytes kept for the backward. */
 int fsnerf_mlp_forward(const fsnerf_net_cfg* cfg, const float* params, const void* packed,
                        int64_t n_samples, int samples_per_ray, const float* rays_o,

@@ -386,3 +386,34 @@ def test_standalone_positional_encoder(dev, golden):
     m = torch.from_numpy(oenc.freq_mask(63, 300, 900)).to(dev)
     np.testing.assert_allclose(pe(x, m).cpu().numpy(), g["pe_pos"] * m.cpu().numpy(), atol=2e-6 * 512)
     assert pe(x[:0]).shape == (0, 63) and pe(x.reshape(2, -1, 3)).shape[:2] == (2, x.shape[0] // 2)
+
+
+@pytest.mark.gpu
+def test_mlp_forward_sigma_slot_and_render_coarse_skip(dev):
+    """density_only=2 writes exactly the sigma of the full forward into raw[:,3]; a hierarchical
+    render whose coarse pass skips the view branch gives bit-identical fine samples and image."""
+    from fsnerf_b200 import ops
+    from fsnerf_b200.engine import HotPath
+    cfg = ops.make_cfg()
+    params = ops.flatten_state_dict(cfg, omlp.init_state_dict(seed=3), dev)
+    packed = ops.mlp_pack(cfg, params)
+    g = torch.Generator().manual_seed(0)
+    x = (torch.rand(1000, 3, generator=g) * 2 - 1).to(dev)
+    d = torch.nn.functional.normalize(torch.randn(1000, 3, generator=g), dim=-1).to(dev)
+    full = ops.mlp_forward(cfg, params, packed, x=x, dirs=d)
+    sig = ops.mlp_forward(cfg, params, packed, x=x, density_only=True)
+    slot = ops.mlp_forward(cfg, params, packed, x=x, density_only=2)
+    assert torch.equal(sig, full[:, 3]) and torch.equal(slot[:, 3], full[:, 3]) and float(slot[:, :3].abs().max()) == 0
+    hp = HotPath(n_coarse=32, n_fine=64, device=dev)
+    o = torch.tensor([0.0, 0.0, 4.0], device=dev).expand(500, 3).contiguous()
+    dd = torch.nn.functional.normalize(torch.tensor([0.0, 0.0, -1.0], device=dev) + 0.2 * torch.randn(500, 3, device=dev), dim=-1)
+    a = hp._forward(o, dd, None, None, train=False)           # coarse pass: sigma only
+    hp.hier_skip = None
+    ts_c, te_c = ops.sample_stratified(500, 32, hp.near, hp.far, None, device=dev)
+    raw_c = ops.mlp_forward(cfg, hp.net_params(0), hp.packed[0], rays_o=o, rays_d=dd, t_starts=ts_c, t_ends=te_c)
+    w_c = ops.composite_forward(raw_c.view(500, 32, 4), ts_c, te_c, bkgd=hp.bkgd)[3]
+    assert torch.equal(a["w_c"], w_c)                          # same weights -> same fine samples
+    ts_f, te_f, *_ = ops.sample_pdf(ts_c, w_c, 64, hp.far, None, want_aux=False)
+    assert torch.equal(a["ts_f"], ts_f)
+    raw_f = ops.mlp_forward(cfg, hp.net_params(1), hp.packed[1], rays_o=o, rays_d=dd, t_starts=ts_f, t_ends=te_f)
+    assert torch.equal(a["rgb"], ops.composite_forward(raw_f.view(500, 96, 4), ts_f, te_f, bkgd=hp.bkgd)[0])
