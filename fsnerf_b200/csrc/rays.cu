@@ -118,11 +118,15 @@ sample_pdf_kernel(int64_t n_rays, int Sc, int Sf, const float* __restrict__ z_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * kPdfWarps + warp;
   const int nb = Sc - 1, nw = Sc - 2, ntot = Sc + Sf;
-  const int per_warp = 2 * nb + 2 * ntot;
+  int P2 = 1;                           // fine samples padded to a power of two for the sort
+  while (P2 < Sf) P2 <<= 1;
+  const int per_warp = 2 * nb + 2 * ntot + 2 * P2;
   float* cdf = smem + warp * per_warp;  // [nb]
   float* bins = cdf + nb;               // [nb]
   float* cat = bins + nb;               // [ntot]
   float* sorted = cat + ntot;           // [ntot]
+  float* fk = sorted + ntot;            // [P2] fine samples, sorted in place
+  int* fi = reinterpret_cast<int*>(fk + P2);  // [P2] their original indices
   if (r >= n_rays) return;
   const float* zc = z_coarse + r * Sc;
   const float* wc = w_coarse + r * Sc;
@@ -196,16 +200,55 @@ sample_pdf_kernel(int64_t n_rays, int Sc, int Sf, const float* __restrict__ z_co
   }
   __syncwarp();
 
-  // stable rank sort of cat[0..ntot): rank = #{j: cat[j] < v or (== and j < i)}
-  for (int i = lane; i < ntot; i += 32) {
-    float v = cat[i];
-    int rank = 0;
-    for (int j = 0; j < ntot; ++j) {
-      float c = cat[j];
-      rank += (c < v || (c == v && j < i)) ? 1 : 0;
+  // stable sort of cat[0..ntot) = merge of the (non-decreasing) coarse points with the fine
+  // samples.  rank(i) = #{j: cat[j] < v or (== and j < i)}, computed as
+  //   * fine samples: bitonic sort by (value, index) in shared memory (O(Sf log^2 Sf));
+  //   * coarse j -> j + #{fine < z_j};  fine at sorted position q -> q + #{coarse <= v}
+  //     (a coarse point precedes an equal fine sample: its index is smaller) by binary search.
+  bool in_order = true;  // deterministic u (evaluation / rendering): the inverse CDF is monotone,
+  for (int q = lane; q < P2; q += 32) {  // the fine samples arrive sorted and the network is skipped
+    const float v = (q < Sf) ? cat[Sc + q] : INFINITY;
+    fk[q] = v;
+    fi[q] = q;
+    if (q > 0 && q < Sf && cat[Sc + q - 1] > v) in_order = false;
+  }
+  in_order = __all_sync(0xffffffffu, in_order);
+  __syncwarp();
+  for (int k = 2; k <= P2 && !in_order; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < (P2 >> 1); t += 32) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int p = i | j;
+        const float a = fk[i], b = fk[p];
+        const int ia = fi[i], ib = fi[p];
+        const bool a_gt_b = (a > b) || (a == b && ia > ib);
+        if (a_gt_b == ((i & k) == 0)) {
+          fk[i] = b; fk[p] = a;
+          fi[i] = ib; fi[p] = ia;
+        }
+      }
+      __syncwarp();
     }
-    sorted[rank] = v;
-    if (perm_out) perm_out[r * ntot + rank] = i;
+  }
+  for (int j = lane; j < Sc; j += 32) {
+    const float v = cat[j];
+    int lo = 0, hi = Sf;  // first fine position with value >= v
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (fk[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    sorted[j + lo] = v;
+    if (perm_out) perm_out[r * ntot + j + lo] = j;
+  }
+  for (int q = lane; q < Sf; q += 32) {
+    const float v = fk[q];
+    int lo = 0, hi = Sc;  // first coarse position with value > v
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cat[mid] <= v) lo = mid + 1; else hi = mid;
+    }
+    sorted[q + lo] = v;
+    if (perm_out) perm_out[r * ntot + q + lo] = Sc + fi[q];
   }
   __syncwarp();
   for (int k = lane; k < ntot; k += 32) {
@@ -313,7 +356,9 @@ extern "C" int fsnerf_sample_pdf(int64_t n_rays, int n_coarse, int n_fine, const
   FS_REQUIRE(n_coarse >= 3 && n_coarse - 2 <= 32 * kPdfMaxE, "sample_pdf: n_coarse must be in [3,258]");
   FS_REQUIRE(n_fine >= 1 && n_fine <= 1024, "sample_pdf: n_fine must be in [1,1024]");
   if (n_rays == 0) return FSNERF_OK;
-  size_t smem = (size_t)kPdfWarps * (2 * (n_coarse - 1) + 2 * (n_coarse + n_fine)) * sizeof(float);
+  int p2 = 1;
+  while (p2 < n_fine) p2 <<= 1;
+  size_t smem = (size_t)kPdfWarps * (2 * (n_coarse - 1) + 2 * (n_coarse + n_fine) + 2 * p2) * sizeof(float);
   FS_REQUIRE(smem <= 48 * 1024, "sample_pdf: n_coarse+n_fine too large for shared memory");
   int64_t blocks = (n_rays + kPdfWarps - 1) / kPdfWarps;
   FsProfScope prof_("sample_pdf", stream);

@@ -61,7 +61,8 @@ int fsnerf_to_ndc(const float* rays_o, const float* rays_d, int64_t n_rays, floa
 int fsnerf_sample_stratified(int64_t n_rays, int n_samples, float near, float far, const float* u,
                              float* t_starts, float* t_ends, void* stream);
 /* Hierarchical inverse-CDF resampling (warp-tree CDF order).
- * z_coarse,w_coarse [R,Sc]; u [R,Sf] or NULL.  Outputs: samples [R,Sf],
+ * z_coarse (non-decreasing per ray, as sample_stratified emits it), w_coarse [R,Sc];
+ * u [R,Sf] or NULL.  Outputs: samples [R,Sf],
  * inds [R,Sf] int32 (searchsorted right), perm [R,Sc+Sf] int32 (stable sort
  * permutation of cat(z_coarse,samples)), t_starts/t_ends [R,Sc+Sf].
  * samples/inds/perm may be NULL. */
