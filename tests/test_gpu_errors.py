@@ -104,3 +104,44 @@ def test_dropin_boundary_errors(dev):
         (rgb, op, dp, ex), ri, tv = render_rays(o, d, est, model, device=dev)
     assert rgb.shape == (16, 3) and ri.dtype == torch.int64 and ri.numel() == 16 * 8 == tv.numel()
     assert set(ex) >= {"weights", "alphas", "trans", "sigmas", "rgbs"}
+
+
+def test_no_out_of_bounds_writes_on_partial_tiles(dev):
+    """compute-sanitizer is not available on the pool: guard bands instead.  Every buffer the MLP
+    kernels write (out, stash, dstash workspace, grads) is followed by a sentinel region that must
+    survive launches on sample counts that are not multiples of the 128-sample tile."""
+    from fsnerf_b200 import ops
+    from oracle import mlp as omlp
+    cfg = ops.make_cfg()
+    params = ops.flatten_state_dict(cfg, omlp.init_state_dict(seed=5), dev)
+    packed = ops.mlp_pack(cfg, params)
+    n_par = ops.mlp_param_count(cfg)
+    G = 4096  # guard bytes / floats
+    for P in (1, 129, 128 * 3 + 77):
+        g = torch.Generator().manual_seed(P)
+        x = (torch.rand(P, 3, generator=g) * 2 - 1).to(dev)
+        d = torch.nn.functional.normalize(torch.randn(P, 3, generator=g), dim=-1).to(dev)
+        out_big = torch.full((P * 4 + G,), 7.25, device=dev)
+        nb_stash, nb_ws = ops.mlp_stash_bytes(cfg, P), ops.mlp_bwd_workspace_bytes(cfg, P)
+        stash_big = torch.full((nb_stash + G,), 0x5A, dtype=torch.uint8, device=dev)
+        ws_big = torch.full((nb_ws + G,), 0xA5, dtype=torch.uint8, device=dev)
+        grads_big = torch.zeros(n_par + G, device=dev)
+        grads_big[n_par:] = -3.5
+        out = ops.mlp_forward(cfg, params, packed, x=x, dirs=d, stash=stash_big[:nb_stash],
+                              out=out_big[:P * 4].view(P, 4))
+        d_out = torch.randn(P, 4, generator=g).to(dev)
+        ops.mlp_backward(cfg, params, packed, P, stash_big[:nb_stash], out, d_out, grads_big[:n_par], ws_big[:nb_ws])
+        torch.cuda.synchronize()
+        assert bool((out_big[P * 4:] == 7.25).all()), P
+        assert bool((stash_big[nb_stash:] == 0x5A).all()), P
+        assert bool((ws_big[nb_ws:] == 0xA5).all()), P
+        assert bool((grads_big[n_par:] == -3.5).all()), P
+        assert torch.isfinite(out).all() and torch.isfinite(grads_big[:n_par]).all()
+        # density-only forms write exactly [P] / the sigma slots
+        sig_big = torch.full((P + G,), 7.25, device=dev)
+        ops.mlp_forward(cfg, params, packed, x=x, density_only=True, out=sig_big[:P])
+        raw_big = torch.full((P * 4 + G,), 7.25, device=dev)
+        ops.mlp_forward(cfg, params, packed, x=x, density_only=2, out=raw_big[:P * 4].view(P, 4))
+        torch.cuda.synchronize()
+        assert bool((sig_big[P:] == 7.25).all()) and torch.equal(sig_big[:P], out[:, 3])
+        assert bool((raw_big[P * 4:] == 7.25).all()) and bool((raw_big[:P * 4].view(P, 4)[:, :3] == 7.25).all())
