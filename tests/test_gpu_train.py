@@ -352,3 +352,46 @@ def test_c3_llff_ndc_freqmask_train_step(dev):
     _check_grad_bar(rels, hp.grads.cpu(), hp, ref_g)
     hp.set_freq_mask(reg_steps, reg_steps)
     assert hp.mask_pos is None and hp.mask_dir is None
+
+
+@pytest.mark.gpu
+def test_c1_coarse_only_train_step(dev):
+    """BASELINE.json configs[0]: 8 views at 100x100 (80 000 rays), coarse-only 8x256 NeRF, 64
+    samples per ray, frequency-mask schedule, one optimisation step of the reference's default batch
+    (1 024 rays, src/utils/parser.py:100) — the fused step vs the oracle step on identical inputs."""
+    from fsnerf_b200 import ops, synthetic as syn
+    from fsnerf_b200.engine import HotPath
+    from oracle import encoding as oenc
+    H = W = 100
+    poses, imgs, focal = syn.make_views(8, H, W, seed=42)
+    R, Sc = 1024, 64
+    rng = np.random.default_rng(21)
+    ids = rng.permutation(8 * H * W)[:R].astype(np.int64)
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    o, d, gt = ops.gen_rays(cu(poses), H, W, focal, pixel_ids=cu(ids), images=cu(imgs))
+    us = rng.random((R, Sc), dtype=f32)
+    hp = HotPath(n_coarse=Sc, n_fine=0, near=2.0, far=6.0, white_bkgd=True, device=dev)
+    assert hp.params.numel() == hp.n_net  # one network
+    step, reg_steps = 100, 900
+    hp.set_freq_mask(step, reg_steps)
+    mp, md = oenc.freq_mask(63, step, reg_steps), oenc.freq_mask(27, step, reg_steps)
+    sd = {k: v.cpu() for k, v in hp.state_dict(0).items()}
+    sd_ref = {k: v.clone() for k, v in sd.items()}
+    ls = hp.train_step(o, d, gt, cu(us), None, lr=5e-4, apply_update=False)
+    grads = hp.grads.clone()
+    ref_loss, ref_psnr, ref_g = orender.train_step(sd_ref, None, dict(step=0, m={}, v={}), o.cpu().numpy(),
+                                                   d.cpu().numpy(), gt.cpu().numpy(), 2.0, 6.0, Sc, 0, us, None,
+                                                   5e-4, True, mask_pos=mp, mask_dir=md)
+    assert float(ls[1]) == 0.0 and abs(ls[0].item() / (3 * R) - ref_loss) < 2e-4
+    assert abs(hp.psnr(ls[0].item(), R) - ref_psnr) < 0.05
+    rels = {}
+    for (off, n), name in zip(hp.layout, hp.names):
+        g_ref = ref_g["c." + name].reshape(-1).double()
+        rels["c." + name] = ((grads[off:off + n].cpu().double() - g_ref).norm() / g_ref.norm().clamp_min(1e-12)).item()
+    print("C1 grad rel err:", {k: round(v, 4) for k, v in rels.items()})
+    for k, r in rels.items():
+        assert r < (1.5e-2 if k.endswith("layers.0.weight") else 1e-2), (k, r)
+    hp.train_step(o, d, gt, cu(us), None, lr=5e-4)  # apply: parameters vs the oracle's Adam step
+    ours = hp.state_dict(0)
+    for k in sd_ref:
+        _check_adam_step(ours[k].cpu(), sd_ref[k], 5e-4, k)
