@@ -119,9 +119,21 @@ class HierarchicalEstimator(nn.Module):
         self.last = {}
         if self.n_fine > 0:
             bk = (torch.ones(3, device=dev) if white_bkgd else None)
-            rgb_c, op_c, dp_c, w_c, *_ = volume_render(self.proposal_model, rays_o, rays_d, ts, te, bk)
-            self.last = dict(rgb_coarse=rgb_c, opacity_coarse=op_c, depth_coarse=dp_c,
-                             weights_coarse=w_c, t_starts_coarse=ts, t_ends_coarse=te)
+            if torch.is_grad_enabled() or stratified:
+                rgb_c, op_c, dp_c, w_c, *_ = volume_render(self.proposal_model, rays_o, rays_d, ts, te, bk)
+                self.last = dict(rgb_coarse=rgb_c, opacity_coarse=op_c, depth_coarse=dp_c,
+                                 weights_coarse=w_c, t_starts_coarse=ts, t_ends_coarse=te)
+            else:
+                # inference (render_frame / render_path / evaluation: train=False under no_grad): only the
+                # WEIGHTS of the proposal pass are needed — skip its view branch (density-only
+                # forward writing sigma into the compositor's (rgb, sigma) layout)
+                pm = self.proposal_model
+                raw_c = ops.mlp_forward(pm.cfg, pm._flat, pm._refresh_packed(), rays_o=rays_o, rays_d=rays_d,
+                                        t_starts=ts, t_ends=te, mask_pos=pm.mask_pos, mask_dir=pm.mask_dir,
+                                        density_only=2)
+                _, op_c, dp_c, w_c, _, _ = ops.composite_forward(raw_c.view(R, self.n_coarse, 4), ts, te, bkgd=bk)
+                self.last = dict(opacity_coarse=op_c, depth_coarse=dp_c, weights_coarse=w_c,
+                                 t_starts_coarse=ts, t_ends_coarse=te)
             if stratified and up is None:
                 up = torch.rand(R, self.n_fine, device=dev)
             ts, te, *_ = ops.sample_pdf(ts, w_c.detach(), self.n_fine, self.far,
@@ -361,6 +373,14 @@ def render_path(render_poses: Tensor, hwf, near: float, far: float, chunksize: i
     total = F * H * W
     start, stop = (total * rank) // world_size, (total * (rank + 1)) // world_size
     frames, d_frames = [], []
+    dev_rgb, dev_dep = [], []
+
+    def flush():  # frames stay on the device and cross to the host in batches: no per-frame sync
+        if dev_rgb:
+            frames.append(torch.cat(dev_rgb).cpu().numpy())
+            d_frames.append(torch.cat(dev_dep).cpu().numpy())
+            dev_rgb.clear()
+            dev_dep.clear()
     with torch.no_grad():
         for i, pose in enumerate(render_poses):
             a, b = max(start, i * H * W), min(stop, (i + 1) * H * W)
@@ -370,9 +390,15 @@ def render_path(render_poses: Tensor, hwf, near: float, far: float, chunksize: i
             rgb, depth = render_frame(hwf, near, far, pose, chunksize, estimator, model, train=train, ndc=ndc,
                                       white_bkgd=white_bkgd, render_step_size=render_step_size,
                                       device=device, pixel_range=rng)
-            frames.append(rgb.reshape(-1, 3).detach().cpu().numpy())
-            d_frames.append(depth.reshape(-1).detach().cpu().numpy())
+            dev_rgb.append(rgb.reshape(-1, 3).detach())
+            dev_dep.append(depth.reshape(-1).detach())
+            if sum(t.shape[0] for t in dev_rgb) >= 64 * 1024 * 1024:  # <= 1 GiB of rgb resident
+                flush()
+        flush()
+    frames = [np.concatenate(frames, 0)] if frames else []
+    d_frames = [np.concatenate(d_frames, 0)] if d_frames else []
     if world_size == 1:
-        return (np.stack([f.reshape(H, W, 3) for f in frames], 0),
-                np.stack([d.reshape(H, W) for d in d_frames], 0))
-    return np.concatenate(frames, 0), np.concatenate(d_frames, 0), (start, stop)
+        return frames[0].reshape(F, H, W, 3), d_frames[0].reshape(F, H, W)
+    if not frames:
+        return np.zeros((0, 3), np.float32), np.zeros((0,), np.float32), (start, stop)
+    return frames[0], d_frames[0], (start, stop)
