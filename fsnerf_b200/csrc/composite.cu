@@ -272,7 +272,7 @@ composite_bwd_kernel(int64_t n_rays, int S, const float4* __restrict__ raw,
 // pass B walks the blocks backwards, re-reads them (L1/L2 hits: a ray is 4.6 KB), recomputes
 // T with the SAME prefix arithmetic as the forward kernel and runs the suffix scan.  Small
 // register state -> 2x the resident warps of the register-resident kernel -> HBM stays busy.
-template <int NB>
+template <int NB, bool kOcc>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 composite_bwd_stream_kernel(int64_t n_rays, int S, const float4* __restrict__ raw,
                             const float* __restrict__ ts, const float* __restrict__ te,
@@ -360,14 +360,14 @@ composite_bwd_stream_kernel(int64_t n_rays, int S, const float4* __restrict__ ra
     const float dsd = g * (T - w) - later;  // T_{i+1} = T_i (1-alpha_i) = T_i - w_i
     float dsig = dsd * delta;
     if (relu && c.w <= 0.f) dsig = 0.f;
-    if (occ.func && s < S) {
+    if (kOcc && s < S) {  // compiled out of the plain kernel: its register count sets the occupancy
       const float ow = occ_weight(occ, tmid);
       dsig = fmaf(occ.scale, ow, dsig);
       occ_acc = fmaf(ow, c.w, occ_acc);
     }
     if (s < S) __stcs(d_raw + base + s, make_float4(w * gr, w * gg, w * gb, dsig));  // write-once stream
   }
-  if (occ.func && occ.loss) {
+  if (kOcc && occ.loss) {
     occ_acc = warp_sum(occ_acc);
     if (lane == 0) atomicAdd(occ.loss, occ_acc);
   }
@@ -457,9 +457,16 @@ static int composite_backward_impl(int64_t n_rays, int n_samples, const float* r
       d_depth, d_weights, d_raw4, d_bkgd, occ)
   FsProfScope prof_("composite_bwd", stream);
 #define LAUNCH_STREAM(NB)                                                                        \
-  composite_bwd_stream_kernel<NB><<<blocks, kWarpsPerBlock * 32, 0, st>>>(                       \
-      n_rays, n_samples, raw4, t_starts, t_ends, delta_scale, bkgd, flags, d_rgb, d_opacity,     \
-      d_depth, d_weights, d_raw4, d_bkgd, occ)
+  do {                                                                                           \
+    if (occ.func)                                                                                \
+      composite_bwd_stream_kernel<NB, true><<<blocks, kWarpsPerBlock * 32, 0, st>>>(             \
+          n_rays, n_samples, raw4, t_starts, t_ends, delta_scale, bkgd, flags, d_rgb, d_opacity, \
+          d_depth, d_weights, d_raw4, d_bkgd, occ);                                              \
+    else                                                                                         \
+      composite_bwd_stream_kernel<NB, false><<<blocks, kWarpsPerBlock * 32, 0, st>>>(            \
+          n_rays, n_samples, raw4, t_starts, t_ends, delta_scale, bkgd, flags, d_rgb, d_opacity, \
+          d_depth, d_weights, d_raw4, d_bkgd, occ);                                              \
+  } while (0)
   if (!(flags & FSNERF_COMP_PRODUCT_TRANS)) {
     if (n_samples <= 64) LAUNCH_STREAM(2);
     else if (n_samples <= 128) LAUNCH_STREAM(4);
