@@ -399,6 +399,34 @@ def main():
                 "fwd": {"ms": f_ms, "achieved": f_bytes / f_ms / 1e6, "frac": f_bytes / f_ms / 1e6 / pk_["hbm"]},
                 "bwd": {"ms": b_ms, "achieved": b_bytes / b_ms / 1e6, "frac": b_bytes / b_ms / 1e6 / pk_["hbm"]}}
         del raw, e_, ts_, te_
+        # sampling kernels (1) at the same scale, against the same HBM roof (algorithmic bytes of SURVEY §8d)
+        us_ = torch.rand(Rc, N_COARSE, device=dev, generator=gcomp)
+        up_ = torch.rand(Rc, N_FINE, device=dev, generator=gcomp)
+        w_ = torch.rand(Rc, N_COARSE, device=dev, generator=gcomp) ** 4
+        for _ in range(2):
+            tsc_, _ = ops.sample_stratified(Rc, N_COARSE, NEAR, FAR, us_)
+            ops.sample_pdf(tsc_, w_, N_FINE, FAR, up_, want_aux=False)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        for _ in range(10):
+            tsc_, _ = ops.sample_stratified(Rc, N_COARSE, NEAR, FAR, us_)
+        ev[1].record()
+        for _ in range(10):
+            ops.sample_pdf(tsc_, w_, N_FINE, FAR, up_, want_aux=False)       # training: random u
+        ev[2].record()
+        for _ in range(10):
+            ops.sample_pdf(tsc_, w_, N_FINE, FAR, None, want_aux=False)      # rendering: deterministic u
+        ev[3].record()
+        torch.cuda.synchronize()
+        st_b = Rc * (24 + 12 * N_COARSE)
+        pdf_b = Rc * (4 * (2 * N_COARSE - 3) + 4 * N_FINE + 8 * (N_COARSE + N_FINE))  # weights, bins, u in; merged intervals out
+        def _roof(b, ms_):
+            return {"ms": ms_, "achieved": b / ms_ / 1e6, "frac": b / ms_ / 1e6 / pk_["hbm"]}
+        comp["sampling"] = {"stratified": _roof(st_b, ev[0].elapsed_time(ev[1]) / 10),
+                            "sample_pdf_random_u": _roof(pdf_b, ev[1].elapsed_time(ev[2]) / 10),
+                            "sample_pdf_deterministic_u": _roof(pdf_b - Rc * 4 * N_FINE, ev[2].elapsed_time(ev[3]) / 10)}
+        del us_, up_, w_
 
     if rank != 0:
         if world > 1:

@@ -90,16 +90,33 @@ __device__ __forceinline__ float strat_point(int i, int S, float near, float far
   return __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), u[i]));
 }
 
-__global__ void stratified_kernel(int64_t n_rays, int S, float near, float far,
-                                  const float* __restrict__ u, float* __restrict__ ts,
-                                  float* __restrict__ te) {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_rays * S) return;
-  int64_t r = idx / S;
-  int i = (int)(idx - r * S);
-  const float* ur = u ? u + r * S : nullptr;
-  ts[idx] = strat_point(i, S, near, far, ur);
-  te[idx] = (i == S - 1) ? far : strat_point(i + 1, S, near, far, ur);
+// HBM bound (24 B/ray + 12 B/sample): the per-stratum bounds depend on the sample index only and
+// are tabulated once per block in shared memory (the IEEE divisions of linspace are the expensive
+// part); every point is computed ONCE and written as t_starts[i] and t_ends[i-1].
+constexpr int kStratMaxS = 2048;
+__global__ void __launch_bounds__(256)
+stratified_kernel(int64_t n_rays, int S, float near, float far, const float* __restrict__ u,
+                  float* __restrict__ ts, float* __restrict__ te, int rays_per_block) {
+  __shared__ float lo[kStratMaxS], hi[kStratMaxS];
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    const float z = strat_z(i, S, near, far);
+    lo[i] = (i == 0) ? z : __fmul_rn(0.5f, __fadd_rn(z, strat_z(i - 1, S, near, far)));
+    hi[i] = (i == S - 1) ? z : __fmul_rn(0.5f, __fadd_rn(strat_z(i + 1, S, near, far), z));
+    if (!u) lo[i] = hi[i] = z;  // deterministic: the points themselves
+  }
+  __syncthreads();
+  const int64_t r0 = (int64_t)blockIdx.x * rays_per_block;
+  const int64_t r1 = (r0 + rays_per_block < n_rays) ? r0 + rays_per_block : n_rays;
+  const int64_t base = r0 * S;
+  const int n = (int)((r1 - r0) * S);
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int i = e % S;
+    const float l = lo[i];
+    const float p = u ? __fadd_rn(l, __fmul_rn(__fsub_rn(hi[i], l), __ldg(u + base + e))) : l;
+    ts[base + e] = p;
+    if (i > 0) te[base + e - 1] = p;
+    if (i == S - 1) te[base + e] = far;
+  }
 }
 
 // ---- sample_pdf (Appendix B2; oracle/sampling.py:sample_pdf) --------------
@@ -269,7 +286,7 @@ extern "C" int fsnerf_gen_rays(const float* poses, int n_views, int pose_rows, i
   FS_REQUIRE(pose_rows == 3 || pose_rows == 4, "gen_rays: pose_rows must be 3 or 4");
   FS_REQUIRE(H > 0 && W > 0 && n_views > 0 && n_rays >= 0, "gen_rays: bad sizes");
   if (n_rays == 0) return FSNERF_OK;
-  int threads = 256;
+  const int threads = 256;
   int64_t blocks = (n_rays + threads - 1) / threads;
   FsProfScope prof_("gen_rays", stream);
   gen_rays_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
@@ -282,7 +299,7 @@ extern "C" int fsnerf_to_ndc(const float* rays_o, const float* rays_d, int64_t n
                              float sx, float sy, float* ndc_o, float* ndc_d, void* stream) {
   if (n_rays == 0) return FSNERF_OK;
   FS_REQUIRE(rays_o && rays_d && ndc_o && ndc_d, "to_ndc: null pointer");
-  int threads = 256;
+  const int threads = 256;
   int64_t blocks = (n_rays + threads - 1) / threads;
   FsProfScope prof_("to_ndc", stream);
   to_ndc_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(rays_o, rays_d, n_rays,
@@ -339,11 +356,13 @@ extern "C" int fsnerf_sample_stratified(int64_t n_rays, int n_samples, float nea
   FS_REQUIRE(n_samples >= 1 && n_rays >= 0, "sample_stratified: bad sizes");
   if (n_rays == 0) return FSNERF_OK;
   FS_REQUIRE(t_starts && t_ends, "sample_stratified: null output");
-  int64_t n = n_rays * n_samples;
-  int threads = 256;
+  FS_REQUIRE(n_samples <= kStratMaxS, "sample_stratified: n_samples must be <= 2048");
   FsProfScope prof_("sample_stratified", stream);
-  stratified_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
-      n_rays, n_samples, near, far, u, t_starts, t_ends);
+  int rays_per_block = 4096 / n_samples;  // ~4 K samples per block, at least one ray
+  if (rays_per_block < 1) rays_per_block = 1;
+  const int64_t blocks = (n_rays + rays_per_block - 1) / rays_per_block;
+  stratified_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n_rays, n_samples, near, far, u, t_starts,
+                                                                       t_ends, rays_per_block);
   return fsnerf_check_launch("sample_stratified");
 }
 
