@@ -82,13 +82,6 @@ __device__ __forceinline__ float strat_z(int i, int S, float near, float far) {
   float t = (S > 1) ? __fdiv_rn((float)i, (float)(S - 1)) : 0.0f;
   return __fadd_rn(__fmul_rn(near, __fsub_rn(1.0f, t)), __fmul_rn(far, t));
 }
-__device__ __forceinline__ float strat_point(int i, int S, float near, float far, const float* u) {
-  float z = strat_z(i, S, near, far);
-  if (!u) return z;
-  float lower = (i == 0) ? z : __fmul_rn(0.5f, __fadd_rn(z, strat_z(i - 1, S, near, far)));
-  float upper = (i == S - 1) ? z : __fmul_rn(0.5f, __fadd_rn(strat_z(i + 1, S, near, far), z));
-  return __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), u[i]));
-}
 
 // HBM bound (24 B/ray + 12 B/sample): the per-stratum bounds depend on the sample index only and
 // are tabulated once per block in shared memory (the IEEE divisions of linspace are the expensive
