@@ -119,6 +119,9 @@ stratified_kernel(int64_t n_rays, int S, float near, float far, const float* __r
 constexpr int kPdfMaxE = 8;  // n_coarse - 2 <= 256
 constexpr int kPdfWarps = 4;
 
+// E = weights per lane = ceil((Sc - 2) / 32), a template parameter so that the unrolled CDF
+// loops (each slot carries an IEEE division) contain no predicated-off slots.
+template <int E>
 __global__ void __launch_bounds__(kPdfWarps * 32)
 sample_pdf_kernel(int64_t n_rays, int Sc, int Sf, const float* __restrict__ z_coarse,
                   const float* __restrict__ w_coarse, const float* __restrict__ u, float far,
@@ -140,36 +143,28 @@ sample_pdf_kernel(int64_t n_rays, int Sc, int Sf, const float* __restrict__ z_co
   if (r >= n_rays) return;
   const float* zc = z_coarse + r * Sc;
   const float* wc = w_coarse + r * Sc;
-  const int E = (nw + 31) / 32;
 
   for (int j = lane; j < nb; j += 32) bins[j] = __fmul_rn(0.5f, __fadd_rn(zc[j + 1], zc[j]));
   for (int j = lane; j < Sc; j += 32) cat[j] = zc[j];
 
-  float wp[kPdfMaxE];
+  float wp[E];
   float s = 0.0f;
 #pragma unroll
-  for (int e = 0; e < kPdfMaxE; ++e) {
-    if (e < E) {
-      int j = lane * E + e;
-      wp[e] = (j < nw) ? __fadd_rn(fmaxf(wc[j + 1], 0.0f), 1e-5f) : 0.0f;
-      s = (e == 0) ? wp[0] : __fadd_rn(s, wp[e]);
-    }
+  for (int e = 0; e < E; ++e) {
+    int j = lane * E + e;
+    wp[e] = (j < nw) ? __fadd_rn(fmaxf(wc[j + 1], 0.0f), 1e-5f) : 0.0f;
+    s = (e == 0) ? wp[0] : __fadd_rn(s, wp[e]);
   }
   float tot = s;
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) tot = __fadd_rn(tot, __shfl_xor_sync(0xffffffffu, tot, m));
-  float loc[kPdfMaxE];
+  float loc[E];
 #pragma unroll
-  for (int e = 0; e < kPdfMaxE; ++e) {
-    if (e < E) {
-      float pdf = __fdiv_rn(wp[e], tot);
-      loc[e] = (e == 0) ? pdf : __fadd_rn(loc[(e + kPdfMaxE - 1) % kPdfMaxE], pdf);
-    }
+  for (int e = 0; e < E; ++e) {
+    float pdf = __fdiv_rn(wp[e], tot);
+    loc[e] = (e == 0) ? pdf : __fadd_rn(loc[e > 0 ? e - 1 : 0], pdf);
   }
-  float T = loc[0];
-#pragma unroll
-  for (int e = 1; e < kPdfMaxE; ++e)
-    if (e < E) T = loc[e];
+  float T = loc[E - 1];
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     float up = __shfl_up_sync(0xffffffffu, T, d);
@@ -181,11 +176,9 @@ sample_pdf_kernel(int64_t n_rays, int Sc, int Sf, const float* __restrict__ z_co
     cdf[0] = 0.0f;
   }
 #pragma unroll
-  for (int e = 0; e < kPdfMaxE; ++e) {
-    if (e < E) {
-      int j = lane * E + e;
-      if (j < nw) cdf[j + 1] = (e == E - 1) ? T : __fadd_rn(excl, loc[e]);
-    }
+  for (int e = 0; e < E; ++e) {
+    int j = lane * E + e;
+    if (j < nw) cdf[j + 1] = (e == E - 1) ? T : __fadd_rn(excl, loc[e]);
   }
   __syncwarp();
 
@@ -374,7 +367,19 @@ extern "C" int fsnerf_sample_pdf(int64_t n_rays, int n_coarse, int n_fine, const
   FS_REQUIRE(smem <= 48 * 1024, "sample_pdf: n_coarse+n_fine too large for shared memory");
   int64_t blocks = (n_rays + kPdfWarps - 1) / kPdfWarps;
   FsProfScope prof_("sample_pdf", stream);
-  sample_pdf_kernel<<<(unsigned)blocks, kPdfWarps * 32, smem, (cudaStream_t)stream>>>(
-      n_rays, n_coarse, n_fine, z_coarse, w_coarse, u, far, samples, inds, perm, t_starts, t_ends);
+#define LAUNCH_PDF(E_)                                                                          \
+  sample_pdf_kernel<E_><<<(unsigned)blocks, kPdfWarps * 32, smem, (cudaStream_t)stream>>>(     \
+      n_rays, n_coarse, n_fine, z_coarse, w_coarse, u, far, samples, inds, perm, t_starts, t_ends)
+  switch ((n_coarse - 2 + 31) / 32) {
+    case 1: LAUNCH_PDF(1); break;
+    case 2: LAUNCH_PDF(2); break;
+    case 3: LAUNCH_PDF(3); break;
+    case 4: LAUNCH_PDF(4); break;
+    case 5: LAUNCH_PDF(5); break;
+    case 6: LAUNCH_PDF(6); break;
+    case 7: LAUNCH_PDF(7); break;
+    default: LAUNCH_PDF(8); break;
+  }
+#undef LAUNCH_PDF
   return fsnerf_check_launch("sample_pdf");
 }
