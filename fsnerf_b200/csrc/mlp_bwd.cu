@@ -461,7 +461,7 @@ struct HeadsArgs {
 // 256 threads: thread t owns 16-byte unit (t & 31) [= 8 features of chunk (t&31)>>3]
 // of the 256-wide h image and, if (t & 31) < 16, of the 128-wide hb image; the 8
 // row-groups (t >> 5) split the 128 rows.  Every load is a coalesced 16 B / lane.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 mlp_heads_wgrad_kernel(const __grid_constant__ HeadsArgs a) {
   __shared__ float4 dsm[kTileM];  // (dz0, dz1, dz2, dsigma) per row
   __shared__ float red[8][32][33];
@@ -471,27 +471,32 @@ mlp_heads_wgrad_kernel(const __grid_constant__ HeadsArgs a) {
   float4 acc_b = make_float4(0.f, 0.f, 0.f, 0.f);  // bias sums: lane 0 of each row group
 #pragma unroll
   for (int e = 0; e < 8; ++e) { acc_s[e] = 0.f; acc_r[0][e] = acc_r[1][e] = acc_r[2][e] = 0.f; }
+  // (dz, dsigma) of this thread's row of the NEXT tile, fetched one tile ahead so that its
+  // latency overlaps the current tile's streaming loop
+  auto load_d = [&](int64_t tile) {
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t p = tile * kTileM + t;
+    if (t < kTileM && tile < a.n_tiles && p < a.n_samples) {
+      const float4 o4 = __ldg(reinterpret_cast<const float4*>(a.out) + p);
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.d_out) + p);
+      d = make_float4(g4.x * o4.x * (1.f - o4.x), g4.y * o4.y * (1.f - o4.y),
+                      g4.z * o4.z * (1.f - o4.z), g4.w);
+    }
+    return d;
+  };
+  float4 d_next = load_d(blockIdx.x);
   for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     __syncthreads();
-    if (t < kTileM) {
-      const int64_t p = tile * kTileM + t;
-      float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p < a.n_samples) {
-        const float4 o4 = __ldg(reinterpret_cast<const float4*>(a.out) + p);
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.d_out) + p);
-        d = make_float4(g4.x * o4.x * (1.f - o4.x), g4.y * o4.y * (1.f - o4.y),
-                        g4.z * o4.z * (1.f - o4.z), g4.w);
-      }
-      dsm[t] = d;
-    }
+    if (t < kTileM) dsm[t] = d_next;
     __syncthreads();
+    d_next = load_d(tile + gridDim.x);
     const uint8_t* rec = a.stash + (size_t)tile * a.stash_tile_bytes;
     const uint8_t* h = rec + a.h_off + chunk * kChunkBytes;
     // lanes with u >= 16 have no hb column: they re-read a valid unit (same cache lines as
     // lanes 0..15) and their rgb partial sums are never used, so the loop stays branch-free
     // and every load of a batch is in flight before the first use
     const uint8_t* hb = rec + a.hb_off + (chunk & 1) * kChunkBytes;
-    constexpr int kBatch = 8;
+    constexpr int kBatch = 4;
 #pragma unroll 1
     for (int r0 = 0; r0 < kTileM / 8; r0 += kBatch) {
       uint4 hv[kBatch], bv[kBatch];
