@@ -187,3 +187,67 @@ def freq_mask(d_out: int, step: int, reg_steps: int) -> Tensor:
     if k < G:
         m[3 * k:3 * k + 3] = ptr - k
     return m
+
+
+# ------------------------------------------------------------------ SiNeRF (module mirror)
+class Sine(nn.Module):
+    """reference: src/core/models.py:145-169 — sin(w x)"""
+
+    def __init__(self, w: float = 1.) -> None:
+        super().__init__()
+        self.w = w
+
+    def forward(self, x: Tensor) -> Tensor:
+        return torch.sin(self.w * x)
+
+
+class SirenLinear(nn.Module):
+    """reference: src/core/models.py:171-236 — Linear + Sine with the SIREN initialisation
+    (uniform(-1/d, 1/d) for the first layer, uniform(-sqrt(6/d), sqrt(6/d)) otherwise; weights
+    drawn before biases, like the reference, so a seeded construction reproduces it)."""
+
+    def __init__(self, in_dim: int = 256, out_dim: int = 256, use_bias: bool = True, w: float = 1.,
+                 is_first: bool = False) -> None:
+        super().__init__()
+        self.fc_layer = nn.Linear(in_dim, out_dim, bias=use_bias)
+        self.use_bias, self.is_first, self.in_dim, self.w, self.c = use_bias, is_first, in_dim, w, 6.
+        self.activation = Sine(w)
+        with torch.no_grad():
+            bound = (1 / in_dim) if is_first else (6. / in_dim) ** 0.5
+            self.fc_layer.weight.uniform_(-bound, bound)
+            if use_bias and self.fc_layer.bias is not None:
+                self.fc_layer.bias.uniform_(-bound, bound)
+
+    def forward(self, x) -> Tensor:
+        return self.activation(self.fc_layer(x))
+
+
+class SiNeRF(nn.Module):
+    """Drop-in for the reference's ``SiNeRF`` (src/core/models.py:238-309; selected by
+    ``--model sinerf``, src/run-nerf.py:81-88): same constructor, state-dict keys and
+    ``forward(x, dirs=None) -> [N,4] = (rgb, relu(sigma))`` or ``[N,1]``.
+
+    NOT on the fused tcgen05 kernels: the sine activations need their own epilogue and a
+    cos-based backward, so this mirror runs on PyTorch's CUDA ops.  It composes with
+    the packed path (``OccGridEstimator`` + ``render_rays``), which calls ``model(x)`` /
+    ``model(x, dirs)`` generically; the hierarchical / fused paths require ``NeRF``."""
+
+    def __init__(self, pos_dim: int = 3, dir_dim: int = 3, width: int = 256,
+                 alpha=(30., 1., 1., 1., 1., 1., 1., 1.)) -> None:
+        super().__init__()
+        self.pos_dim, self.dir_dim, self.alpha = pos_dim, dir_dim, list(alpha)
+        hidden = [SirenLinear(width, width, True, a) for a in self.alpha[1:]]
+        self.first_layers = nn.Sequential(SirenLinear(pos_dim, width, True, self.alpha[0], True), *hidden)
+        self.sigma_layers = nn.Sequential(SirenLinear(width, width // 2, True), nn.Linear(width // 2, 1, True),
+                                          nn.ReLU())
+        self.fc_feature = nn.Linear(width, width)
+        self.rgb_layers = nn.Sequential(SirenLinear(width + dir_dim, width // 2, True),
+                                        nn.Linear(width // 2, 3, True), nn.Sigmoid())
+
+    def forward(self, x: Tensor, dirs: Tensor = None) -> Tensor:
+        x = self.first_layers(x)
+        if dirs is None:
+            return self.sigma_layers(x)
+        sigma = self.sigma_layers(x)
+        x = torch.cat([self.fc_feature(x), dirs], dim=-1)
+        return torch.cat([self.rgb_layers(x), sigma], dim=-1)

@@ -427,3 +427,24 @@ def test_occgrid_oracle_known_answers():
     assert thre == 1e-2 and list(b) == [True, True, False, True]
     b, thre = oocc.binarize(np.array([0.001, 0.003, 0.0, 0.0], np.float32), 1e-2)
     assert abs(thre - 0.001) < 1e-9 and list(b) == [False, True, False, False]
+
+
+def test_sinerf_mirror_matches_reference(golden):
+    """fsnerf_b200.core.models.SiNeRF (torch-op module mirror) vs the reference's SiNeRF: seeded
+    construction, state dict, forward values and gradient norms (fixture: oracle/gen_golden_sinerf.py)"""
+    from fsnerf_b200.core.models import SiNeRF
+    g = golden("reference_sinerf.npz")
+    torch.manual_seed(42)
+    model = SiNeRF(3, 3, 256, [30.] + [1.] * 7)
+    sd = model.state_dict()
+    assert list(sd.keys()) == [str(n) for n in g["names"]]
+    for i, (k, v) in enumerate(sd.items()):
+        assert str(tuple(v.shape)) == str(g["shapes"][i]), k
+        assert abs(v.double().sum().item() - g["w_sum"][i]) < 1e-9 and abs(v.double().abs().sum().item() - g["w_abs"][i]) < 1e-9, k
+    x, d = torch.from_numpy(g["x"]), torch.from_numpy(g["d"])
+    out = model(x, d)
+    np.testing.assert_allclose(out.detach().numpy(), g["out"], atol=1e-6)
+    np.testing.assert_allclose(model(x).detach().numpy(), g["sigma_only"], atol=1e-6)
+    loss = (out * torch.linspace(0.1, 1.0, 4)).sum()
+    grads = torch.autograd.grad(loss, list(model.parameters()))
+    np.testing.assert_allclose([gr.double().norm().item() for gr in grads], g["g_norm"], rtol=1e-5, atol=1e-9)
