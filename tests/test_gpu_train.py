@@ -3,6 +3,8 @@ against the CPU oracle on identical inputs and uniforms.  Bars from
 BASELINE.json north_star: ray/pixel bookkeeping bit-exact; per-ray rgb, depth,
 opacity within 1e-3 absolute; MLP weight gradients within 1e-2 relative; PSNR
 after a fixed step count within 0.1 dB."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -395,3 +397,21 @@ def test_c1_coarse_only_train_step(dev):
     ours = hp.state_dict(0)
     for k in sd_ref:
         _check_adam_step(ours[k].cpu(), sd_ref[k], 5e-4, k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sampler", ["hierarchical", "occgrid"])
+def test_reference_run_loop_on_dropin_modules(dev, sampler, tmp_path):
+    """examples/train_dropin.py = the reference's run loop (src/run-nerf.py main/train/evaluation)
+    on the drop-in modules only: scene on disk -> loaders -> train -> eval -> checkpoint -> render_path."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("train_dropin", os.path.join(
+        os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "train_dropin.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    res = mod.main(["--iters", "150", "--size", "32", "--views", "6", "--batch", "512", "--sampler", sampler,
+                    "--out", str(tmp_path)])
+    assert res["train_psnr_last"] > res["train_psnr_first"] + 2.0, res  # it learns the scene
+    assert np.isfinite(res["val_psnr"]) and 0.0 < res["val_ssim"] <= 1.0
+    assert res["frames"] == (3, 32, 32, 3) and res["d_frames"] == (3, 32, 32)
+    assert os.path.exists(res["checkpoint"]) and abs(res["lr_final"] - 5e-5) < 1e-6
