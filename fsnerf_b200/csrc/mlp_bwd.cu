@@ -620,14 +620,6 @@ extern "C" int fsnerf_mlp_backward(const fsnerf_net_cfg* cfg, const float* param
   ba.stash = reinterpret_cast<const uint8_t*>(stash); ba.out = out; ba.d_out = d_out;
   ba.grads = grads; ba.dstash = reinterpret_cast<uint8_t*>(workspace);
   int grid = (int)(n_tiles < 2 * kNumSMs ? n_tiles : 2 * kNumSMs);
-  {
-    cudaError_t e = cudaMemcpyToSymbolAsync(c_small, ba.packed + P.small_off, kSmallFloats * sizeof(float), 0,
-                                            cudaMemcpyDeviceToDevice, st);
-    if (e != cudaSuccess) {
-      fsnerf_set_error("mlp_backward: constant upload: %s", cudaGetErrorString(e));
-      return FSNERF_ERR_CUDA;
-    }
-  }
   static int variant = -1;  // FSNERF_BWD_VARIANT: unset / 2 = tensor-memory dgrad (mlp_bwd2.cu), 1 = first generation
   if (variant < 0) {
     const char* e = getenv("FSNERF_BWD_VARIANT");
@@ -640,6 +632,14 @@ extern "C" int fsnerf_mlp_backward(const fsnerf_net_cfg* cfg, const float* param
   if (variant == 2) {
     rc = mlp_dgrad_v2(P, packed, n_samples, stash, out, d_out, grads, workspace, stream);
   } else {
+    {
+      cudaError_t e = cudaMemcpyToSymbolAsync(c_small, ba.packed + P.small_off, kSmallFloats * sizeof(float), 0,
+                                              cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) {
+        fsnerf_set_error("mlp_backward: constant upload: %s", cudaGetErrorString(e));
+        return FSNERF_ERR_CUDA;
+      }
+    }
     {
       FsProfScope prof_("mlp_dgrad", stream);
       mlp_dgrad_kernel<<<grid, kThreads, kSmemTotal, st>>>(P, BP, ba);

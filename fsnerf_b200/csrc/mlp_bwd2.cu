@@ -50,7 +50,6 @@ struct BarsB {
   static constexpr int tmem_slot = slab_free + 8 * 4 * kStageBufsB;
 };
 
-__constant__ float c_smallB[kSmallFloats];
 
 struct StepB {
   int target;      // layer whose d(pre-activation) this step produces
@@ -116,8 +115,11 @@ mlp_dgrad2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant
     tmem_relinquish();
   }
   for (int i = threadIdx.x; i < kMaxLayersB * 256; i += kThreadsB) bias_acc[i] = 0.f;
-  for (int i = threadIdx.x; i < 640; i += kThreadsB)
-    reinterpret_cast<float*>(smem + SmemB::heads)[i] = c_smallB[kSmallSigmaW + i];
+  {  // head weights straight from the packed image's fp32 small-params block (no constant upload)
+    const float* __restrict__ small = reinterpret_cast<const float*>(args.packed + prog.small_off);
+    for (int i = threadIdx.x; i < 640; i += kThreadsB)
+      reinterpret_cast<float*>(smem + SmemB::heads)[i] = __ldg(small + kSmallSigmaW + i);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -397,12 +399,6 @@ int mlp_dgrad_v2(const MlpProgram& P, const void* packed, int64_t n_samples, con
   }
   const int64_t n_tiles = (n_samples + kTileM - 1) / kTileM;
   const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
-  cudaError_t e = cudaMemcpyToSymbolAsync(c_smallB, a.packed + P.small_off, kSmallFloats * sizeof(float), 0,
-                                          cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
-  if (e != cudaSuccess) {
-    fsnerf_set_error("mlp_backward: constant upload: %s", cudaGetErrorString(e));
-    return FSNERF_ERR_CUDA;
-  }
   FsProfScope prof_("mlp_dgrad", stream);
   mlp_dgrad2_kernel<<<grid, kThreadsB, SmemB::total, (cudaStream_t)stream>>>(P, PL, a, T);
   return fsnerf_check_launch("mlp_backward(dgrad)");

@@ -47,7 +47,7 @@ template <bool kTrain> struct Smem {
   static constexpr int exch = staging + (kTrain ? 4 * kStageBufs * kSlabBytes2 : 0);
   static constexpr int bias = exch + kTileM * 16;              // fp32 [kMaxLayers2][256]
   static constexpr int heads = bias + kMaxLayers2 * 256 * 4;   // fp32 sigma_w[256], rgb_w[3][128]
-  static constexpr int bars = heads + 640 * 4;
+  static constexpr int bars = heads + 648 * 4;                 // + sigma_b, rgb_b[3] (contiguous in the small block)
   static constexpr int total = bars + 256;
 };
 
@@ -66,7 +66,6 @@ template <bool kTrain> struct Bars {
   static constexpr int tmem_slot = token + 16;
 };
 
-__constant__ float c_small2[kSmallFloats];
 
 #define FS_TRACE2(slot, g_, k_)                                                             \
   do {                                                                                      \
@@ -147,10 +146,13 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
   }
   // biases: constant bank -> shared memory (the epilogue reads them as broadcast LDS.128;
   // indexed constant loads miss the small constant cache and serialise the epilogue)
+  // straight from the packed image's fp32 "small params" block (no per-launch constant upload)
+  const float* __restrict__ small = reinterpret_cast<const float*>(args.packed + prog.small_off);
   for (int i = threadIdx.x; i < prog.n_gemm * 256; i += kThreads2)
-    reinterpret_cast<float*>(smem + S::bias)[i] = c_small2[kSmallBias + i];
-  for (int i = threadIdx.x; i < 640; i += kThreads2)  // sigma_w[256] then rgb_w[3][128]: contiguous in the block
-    reinterpret_cast<float*>(smem + S::heads)[i] = c_small2[kSmallSigmaW + i];
+    reinterpret_cast<float*>(smem + S::bias)[i] = __ldg(small + kSmallBias + i);
+  for (int i = threadIdx.x; i < 644; i += kThreads2)  // sigma_w[256], rgb_w[3][128], sigma_b, rgb_b[3]: contiguous
+    reinterpret_cast<float*>(smem + S::heads)[i] = __ldg(small + kSmallSigmaW + i);
+  const float* head_b = reinterpret_cast<const float*>(smem + S::heads) + 640;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -345,7 +347,7 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
         if (epi == EPI_RELU_SIGMA) {
           if (half == 1) exch[row].w = sig_part;
           named_bar_sync(1 + quarter, 64);
-          if (half == 0) sigma = sig_part + exch[row].w + c_small2[kSmallSigmaB];
+          if (half == 0) sigma = sig_part + exch[row].w + head_b[0];
           // density_only: 1 -> out [P]; 2 -> the sigma slot of a [P,4] (rgb, sigma) buffer
           if (last && half == 0 && valid) args.out[args.density_only == 2 ? 4 * p + 3 : p] = sigma;
         } else if (epi == EPI_BRANCH) {
@@ -355,9 +357,9 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
           named_bar_sync(1 + quarter, 64);
           if (half == 0 && valid) {
             const float4 e = exch[row];
-            const float z0 = part[0] + e.x + c_small2[kSmallRgbB + 0];
-            const float z1 = part[1] + e.y + c_small2[kSmallRgbB + 1];
-            const float z2 = part[2] + e.z + c_small2[kSmallRgbB + 2];
+            const float z0 = part[0] + e.x + head_b[1];
+            const float z1 = part[1] + e.y + head_b[2];
+            const float z2 = part[2] + e.z + head_b[3];
             reinterpret_cast<float4*>(args.out)[p] =
                 make_float4(1.0f / (1.0f + expf(-z0)), 1.0f / (1.0f + expf(-z1)), 1.0f / (1.0f + expf(-z2)), sigma);
           }
@@ -448,13 +450,7 @@ int mlp_forward_v2(const MlpProgram& P, const void* packed, int64_t n_samples, i
   }
   const int64_t n_tiles = (n_samples + kTileM - 1) / kTileM;
   const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
-  cudaError_t e = cudaMemcpyToSymbolAsync(c_small2, a.packed + P.small_off, kSmallFloats * sizeof(float), 0,
-                                          cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
-  if (e != cudaSuccess) {
-    fsnerf_set_error("mlp_forward: constant upload: %s", cudaGetErrorString(e));
-    return FSNERF_ERR_CUDA;
-  }
-  FsProfScope prof_(stash ? "mlp_fwd_train" : "mlp_fwd", stream);
+FsProfScope prof_(stash ? "mlp_fwd_train" : "mlp_fwd", stream);
   if (stash)
     mlp_fwd2_kernel<true><<<grid, kThreads2, Smem<true>::total, (cudaStream_t)stream>>>(P, a, T);
   else
