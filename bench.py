@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-dropin", action="store_true")
+    ap.add_argument("--no-micro", action="store_true", help="skip the render-scale compositing / sampling rooflines")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -374,7 +375,7 @@ def main():
     # ---- compositing kernel at render scale (HBM roofline of kernel (4); SURVEY.md §7 "hard parts":
     #      at training sizes it is launch-latency bound and L2 resident)
     comp = None
-    if rank == 0:
+    if rank == 0 and not args.no_micro:
         Rc, Sc_ = 262144, N_COARSE + N_FINE
         gcomp = torch.Generator(device=dev).manual_seed(0)
         raw = torch.rand(Rc, Sc_, 4, device=dev, generator=gcomp)
