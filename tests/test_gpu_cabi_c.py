@@ -9,6 +9,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _compile(out):
+    if not os.path.exists(os.path.join(ROOT, "fsnerf_b200", "libfsnerf_b200.so")):
+        import sys
+        sys.path.insert(0, ROOT)
+        import __graft_entry__
+        __graft_entry__.build()
     cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
     cmd = ["gcc", "-O2", "-std=c11", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
            os.path.join(ROOT, "tests", "cabi_smoke.c"), "-o", out, "-L", os.path.join(ROOT, "fsnerf_b200"),
