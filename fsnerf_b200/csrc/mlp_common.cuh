@@ -92,10 +92,4 @@ int mlp_forward_v2(const MlpProgram& P, const void* packed, int64_t n_samples, i
                    const float* x, const float* dirs, const float* mask_pos, const float* mask_dir,
                    int density_only, float* out, void* stash, void* stream);
 
-// second-generation dgrad (mlp_bwd2.cu): d(pre-activation) chain resident in tensor memory;
-// writes the dpre images to `workspace` (same layout as the first generation) and
-// accumulates the bias gradients into `grads`
-int mlp_dgrad_v2(const MlpProgram& P, const void* packed, int64_t n_samples, const void* stash, const float* out,
-                 const float* d_out, float* grads, void* workspace, void* stream);
-
 }  // namespace fs

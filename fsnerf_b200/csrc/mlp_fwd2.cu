@@ -161,14 +161,14 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
   if (warp >= kWarpProd0) {
     // ------------------------------------------------ weight producers
     IssueBars IB{bar_w_full, bar_w_empty, bar_token, sbase + S::ring};
-    producer_loop<kStages>(tab, IB, args.packed, n_tiles, warp - kWarpProd0, lane);
+    producer_loop<kStages>(tab, IB, args.packed, n_tiles, warp - kWarpProd0, lane, blockIdx.x, gridDim.x);
   } else if (warp >= kWarpMma) {
     // ------------------------------------------------ MMA issuers (mlp_issue.cuh)
     // Within a layer the encoding chunk (smem operand, independent of the previous epilogue)
     // goes FIRST in the table: it fills the bubble while the epilogue converts chunk 0.
     if (tmem_base != 0) __trap();  // 512 columns = the whole tensor memory
     IssueBars IB{bar_w_full, bar_w_empty, bar_token, sbase + S::ring};
-    issuer_loop<kStages>(tab, IB, sbase, n_tiles, (uint32_t)(warp - kWarpMma), lane, args.trace);
+    issuer_loop<kStages>(tab, IB, sbase, n_tiles, (uint32_t)(warp - kWarpMma), lane, args.trace, blockIdx.x, gridDim.x);
   } else if (warp >= kWarpEnc0) {
     // ------------------------------------------------ encoders (thread = sample row)
     const int row = (warp - kWarpEnc0) * 32 + lane;
@@ -379,17 +379,21 @@ int mlp_forward_v2(const MlpProgram& P, const void* packed, int64_t n_samples, i
                    const float* rays_o, const float* rays_d, const float* t_starts, const float* t_ends,
                    const float* x, const float* dirs, const float* mask_pos, const float* mask_dir,
                    int density_only, float* out, void* stash, void* stream) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e1 = cudaFuncSetAttribute(mlp_fwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          Smem<false>::total);
-    cudaError_t e2 = cudaFuncSetAttribute(mlp_fwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          Smem<true>::total);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) {
-      fsnerf_set_error("mlp_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-      return FSNERF_ERR_CUDA;
+  {  // function attributes are per device
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      cudaError_t e1 = cudaFuncSetAttribute(mlp_fwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            Smem<false>::total);
+      cudaError_t e2 = cudaFuncSetAttribute(mlp_fwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            Smem<true>::total);
+      if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        fsnerf_set_error("mlp_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        return FSNERF_ERR_CUDA;
+      }
+      if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    configured = true;
   }
   Fwd2Args a;
   a.trace = reinterpret_cast<long long*>(fsnerf_debug_trace_ptr());
@@ -399,7 +403,8 @@ int mlp_forward_v2(const MlpProgram& P, const void* packed, int64_t n_samples, i
   a.x = x; a.dirs = dirs; a.mask_pos = mask_pos; a.mask_dir = mask_dir;
   a.density_only = density_only; a.out = out; a.stash = reinterpret_cast<uint8_t*>(stash);
   FS_REQUIRE(P.n_gemm <= kMaxLayers2, "mlp_forward: at most %d GEMM layers are supported", kMaxLayers2);
-  static IssueTable T;  // host staging (one host thread per device, see header)
+  IssueTable T;
+  T.pad = 0;
   {
     const bool train = stash != nullptr;
     const int n_gemm = density_only ? P.n_hidden : P.n_gemm;
@@ -439,6 +444,7 @@ int mlp_forward_v2(const MlpProgram& P, const void* packed, int64_t n_samples, i
         R.n_acc = issue_n_acc(i, nch);
         R.w_block = (uint32_t)(L.first_block + (c >= 0 ? c : L.n_act_chunks) * L.n_halves);
         R.w_bytes = (uint32_t)L.n_halves * kBlockBytes;
+        R.pad[0] = R.pad[1] = R.pad[2] = 0;
       }
       if (L.n_act_chunks) ++cons;
     }
@@ -459,3 +465,34 @@ FsProfScope prof_(stash ? "mlp_fwd_train" : "mlp_fwd", stream);
 }
 
 }  // namespace fs
+
+using namespace fs;
+
+extern "C" int fsnerf_mlp_forward(const fsnerf_net_cfg* cfg, const float* params,
+                                  const void* packed, int64_t n_samples, int samples_per_ray,
+                                  const float* rays_o, const float* rays_d, const float* t_starts,
+                                  const float* t_ends, const float* x, const float* dirs,
+                                  const float* mask_pos, const float* mask_dir, int density_only,
+                                  float* out, void* stash, void* stream) {
+  MlpProgram P;
+  int rc = build_program(cfg, &P);
+  if (rc != FSNERF_OK) return rc;
+  FS_REQUIRE(n_samples >= 0, "mlp_forward: negative n_samples");
+  FS_REQUIRE(density_only >= 0 && density_only <= 2, "mlp_forward: density_only must be 0, 1 or 2");
+  if (n_samples == 0) return FSNERF_OK;
+  FS_REQUIRE(params && packed && out, "mlp_forward: null pointer");
+  if (x) {
+    FS_REQUIRE(density_only || dirs, "mlp_forward: dirs required unless density_only");
+  } else {
+    FS_REQUIRE(rays_o && rays_d && t_starts && t_ends && samples_per_ray > 0,
+               "mlp_forward: rays/t_starts/t_ends required when x is NULL");
+  }
+  FS_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127) == 0 &&
+                 (reinterpret_cast<uintptr_t>(params) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(stash) & 127) == 0,
+             "mlp_forward: params/out must be 16B aligned, packed/stash 128B aligned");
+  FS_REQUIRE(!(stash && density_only), "mlp_forward: stash (training) needs the full network");
+  return mlp_forward_v2(P, packed, n_samples, samples_per_ray, rays_o, rays_d, t_starts, t_ends, x, dirs,
+                        mask_pos, mask_dir, density_only, out, stash, stream);
+}

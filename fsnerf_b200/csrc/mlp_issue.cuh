@@ -90,9 +90,9 @@ __host__ __device__ __forceinline__ uint32_t relu_bits_word_off(int chunk, int h
 // Producer `me` of kProdWarps streams every kProdWarps-th stage: L2 -> smem, one bulk copy.
 template <int kStages>
 __device__ __forceinline__ void producer_loop(const IssueTable& tab, const IssueBars& B, const uint8_t* packed,
-                                              int64_t n_tiles, int me, int lane) {
+                                              int64_t n_tiles, int me, int lane, int64_t tile0, int64_t tile_stride) {
   uint32_t cnt = 0;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
     for (int j = 0; j < tab.n; ++j, ++cnt) {
       if ((int)(cnt % kProdWarps) != me) continue;
       const uint32_t stage = cnt % kStages, phase = (cnt / kStages) & 1;
@@ -108,19 +108,39 @@ __device__ __forceinline__ void producer_loop(const IssueTable& tab, const Issue
   }
 }
 
+// Single-thread form: thread `me` of kProdWarps issuing threads (lanes of ONE warp, each on its
+// own divergent path) streams every kProdWarps-th stage.
+template <int kStages>
+__device__ __forceinline__ void producer_loop_thread(const IssueTable& tab, const IssueBars& B, const uint8_t* packed,
+                                                     int64_t n_tiles, int me, int64_t tile0, int64_t tile_stride) {
+  uint32_t cnt = 0;
+  for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
+    for (int j = 0; j < tab.n; ++j, ++cnt) {
+      if ((int)(cnt % kProdWarps) != me) continue;
+      const uint32_t stage = cnt % kStages, phase = (cnt / kStages) & 1;
+      mbar_wait_relaxed(B.w_empty + 8 * stage, phase ^ 1);
+      const uint32_t bytes = tab.rec[j].w_bytes;
+      mbar_arrive_expect_tx(B.w_full + 8 * stage, bytes);
+      bulk_g2s(B.ring + stage * kStageBytes, packed + (size_t)tab.rec[j].w_block * kBlockBytes, bytes,
+               B.w_full + 8 * stage);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ MMA issuers
 // All 32 lanes of issuer `me` run this loop in lock step on provably uniform values; the
 // tcgen05 instructions are guarded so that lane 0 alone issues them.  trace: optional
 // clock64 timeline [tile iteration < 4][layer][k]: k = 0 layer reached, 1 first MMA, 2 committed.
 template <int kStages>
 __device__ __forceinline__ void issuer_loop(const IssueTable& tab, const IssueBars& B, uint32_t sbase,
-                                            int64_t n_tiles, uint32_t me, int lane, long long* trace) {
+                                            int64_t n_tiles, uint32_t me, int lane, long long* trace,
+                                            int64_t tile0, int64_t tile_stride) {
   const uint32_t issue = (lane == 0) ? 1u : 0u;
   const int n_rec = tab.n;
-  int64_t tile = blockIdx.x;
+  int64_t tile = tile0;
   uint32_t titer = 0;
   int j = (int)me;
-  if (j >= n_rec) { j -= n_rec; tile += gridDim.x; ++titer; }
+  if (j >= n_rec) { j -= n_rec; tile += tile_stride; ++titer; }
   uint32_t stage = me % kStages, wpar = 0, tok_par = me ? 0u : 1u;
   const bool tr = trace != nullptr && blockIdx.x == 0 && lane == 0;
   while (tile < n_tiles) {
@@ -165,7 +185,7 @@ __device__ __forceinline__ void issuer_loop(const IssueTable& tab, const IssueBa
     stage += kMmaWarps;
     if (stage >= (uint32_t)kStages) { stage -= kStages; wpar ^= 1u; }
     if (j >= n_rec) {
-      j -= n_rec; tile += gridDim.x;
+      j -= n_rec; tile += tile_stride;
       // the next tile's first layer overwrites TMEM region 0, which the last layer still reads
       // as its A operand: let the tensor pipe drain first (that barrier completes last_acc_n
       // times per tile)

@@ -35,6 +35,32 @@ def allreduce_gradients(flat_grads: torch.Tensor, group=None) -> torch.Tensor:
     return flat_grads
 
 
+def allreduce_module_gradients(models, group=None) -> None:
+    """Data-parallel exchange for the reference-style loop (``loss.backward()`` on the drop-in
+    modules, then ``optimizer.step()``): SUM of every parameter gradient over the ranks.  A drop-in
+    ``NeRF``'s gradients are views of ONE flat buffer written by its backward kernels, so each
+    network costs one collective; any other module falls back to a coalesced copy."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return
+    for m in models:
+        flat = getattr(m, "_last_flat_grad", None)
+        params = [p for p in m.parameters() if p.grad is not None]
+        if flat is not None and hasattr(m, "_layout") and len(params) == len(m._layout) and all(
+                p.grad.data_ptr() == flat.data_ptr() + 4 * o and p.grad.is_contiguous()
+                for (o, _), p in zip(m._layout, m._param_list())):
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            continue
+        if not params:
+            continue
+        buf = torch.cat([p.grad.reshape(-1) for p in params])
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        o = 0
+        for p in params:
+            n = p.grad.numel()
+            p.grad.copy_(buf[o:o + n].view_as(p.grad))
+            o += n
+
+
 def pixel_partition(n_frames: int, H: int, W: int, rank: int, world: int):
     """per-frame flattened pixel ranges rendered by `rank`:
     [(frame, first_pixel, last_pixel_exclusive), ...] covering its slice of F*H*W"""

@@ -1,0 +1,50 @@
+"""Where the CTAs of the fused MLP backward wait (tuning aid): per-role cycle counters that the
+kernel accumulates when a trace buffer is set (csrc/mlp_bwd2.cu: kStatBase)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fsnerf_b200 import _lib  # noqa: E402
+from fsnerf_b200.engine import HotPath  # noqa: E402
+
+dev = torch.device("cuda:0")
+hp = HotPath(device=dev)
+R = 4096
+g = torch.Generator().manual_seed(0)
+o = (torch.tensor([0.0, 0, 4.0]) + 0.05 * torch.randn(R, 3, generator=g)).to(dev)
+d = torch.nn.functional.normalize(torch.tensor([0.0, 0, -1.0]) + 0.3 * torch.randn(R, 3, generator=g), dim=-1).to(dev)
+gt = torch.rand(R, 3, generator=g).to(dev)
+for _ in range(2):
+    hp.train_step(o, d, gt)
+torch.cuda.synchronize()
+trace = torch.zeros(8192, dtype=torch.int64, device=dev)
+_lib.load().fsnerf_debug_set_trace(_lib.ptr(trace))
+hp.train_step(o, d, gt)   # the fine pass (last) overwrites the coarse pass's counters
+torch.cuda.synchronize()
+_lib.load().fsnerf_debug_set_trace(None)
+s = trace.cpu()[1024:1024 + 148 * 8].view(148, 8).double() / 1e3
+n_w = int(os.environ.get("FSNERF_BWD_WGRAD_CTAS", "50"))
+n_d = 148 - n_w
+dg, wg = s[:n_d], s[n_d:]
+print(f"dgrad CTAs ({n_d}), kcycles mean [min..max]:")
+for k, name in [(0, "total"), (1, "store warp: ring slot (cons) wait"), (2, "store warp: staged slab wait"),
+                (5, "store warp: publish (barrier + fence)"), (3, "epilogue: staging buffer wait"),
+                (4, "epilogue: accumulator wait")]:
+    c = dg[:, k]
+    print(f"  {name:40s} {c.mean():9.1f} [{c.min():9.1f} .. {c.max():9.1f}]")
+print(f"wgrad CTAs ({n_w}), per job: CTAs, tiles/CTA, total kcyc, producer ready-wait, producer empty-wait, MMA full-wait")
+for j in sorted(set(int(x) for x in (wg[:, 6] * 1e3).round().tolist())):
+    m = (wg[:, 6] * 1e3).round() == j
+    r = wg[m]
+    print(f"  job {j:2d}: {int(m.sum()):3d} {r[:, 4].mean() * 1e3:7.0f} {r[:, 0].mean():9.1f} {r[:, 1].mean():9.1f} "
+          f"{r[:, 2].mean():9.1f} {r[:, 3].mean():9.1f}")
+
+# life of the first images of dgrad CTA 0 (global timer, us relative to the first event)
+e = trace.cpu()[4096:4096 + 7 * 256].view(7, 256).double()
+t0 = e[e > 0].min()
+names = ["slot_wait", "slot_ok", "done", "published", "scouted", "issued", "released"]
+print("image q (tile iter * 10 + image): " + " ".join(f"{n:>10s}" for n in names) + "   (us; images with two readers have no issue/release stamps)")
+for q in list(range(0, 40)) + list(range(100, 120)):
+    print(f"  q={q:3d} " + " ".join(f"{(e[k, q] - t0) / 1e3:10.1f}" if e[k, q] > 0 else "         -" for k in range(7)))
