@@ -10,7 +10,7 @@
 //                   PLACE as the next step's A operand; every finished chunk is handed to the
 //                   MMA warps and staged through smem per 32-row slab
 //      warps 8..11  store warps: copy each staged slab into the CTA's private ring of dpre
-//                   images (below) and column-sum it into the bias gradients
+//                   images (below)
 //      warps 12,13  MMA issuers, alternating chunks (mlp_issue.cuh): D[128 x 256] = dpre . W
 //      warp 14      weight producers: two lanes, alternating W^T operand stages (L2 -> smem
 //                   bulk copies)
@@ -21,7 +21,10 @@
 //    dW[N_out x K_in] += dpre^T . X accumulated in TENSOR MEMORY over every tile it is dealt
 //    (jobs with several CTAs interleave the tiles) and flushed ONCE with fp32 atomics.  Both
 //    operands are [samples x features] SWIZZLE_128B images used MN-major: X from the forward
-//    stash (HBM, read once), dpre from the ring.
+//    stash (HBM, read once), dpre from the ring.  Eight more warps of the CTA take what the
+//    tensor core does not: the layer's bias gradient (column sums of the dpre slabs) and, in the
+//    two jobs that have the inputs in shared memory, the degenerate sigma / rgb head weight
+//    gradients (N = 1 / 3) on CUDA cores, all accumulated in registers over the whole launch.
 //
 //  The ring replaces round 1's full-size dstash workspace (4.9 KB/sample written by dgrad and
 //  read back by wgrad through HBM: 16 GB per C2 step).  Each dgrad CTA owns `depth` 64 KB
@@ -49,7 +52,7 @@ constexpr int kWarpMmaB = kEpiWarpsB + kRedWarpsB;    // 12, 13
 constexpr int kWarpProdB = kWarpMmaB + kMmaWarps;     // 14
 constexpr int kWarpRingB = kWarpProdB + 1;            // 15
 constexpr int kThreadsB = (kWarpRingB + 1) * 32;      // 512
-constexpr int kImgBars = 16;                          // image-written barriers (>= max ring depth)
+constexpr int kImgBars = 32;                          // image-written barriers (>= max ring depth)
 constexpr int kStagesB = 4;
 constexpr int kSlabBytesB = 32 * 128;
 constexpr int kStageBufsB = 3;
@@ -62,7 +65,7 @@ struct SmemB {
   static constexpr int bias = staging + 4 * kStageBufsB * kSlabBytesB;   // fp32 [kMaxLayersB][256]
   static constexpr int heads = bias + kMaxLayersB * 256 * 4;             // sigma_w[256], rgb_w[3][128]
   static constexpr int bars = heads + 640 * 4;
-  static constexpr int total = bars + 512;
+  static constexpr int total = bars + 768;
 };
 struct BarsB {
   static constexpr int w_full = SmemB::bars;
@@ -99,6 +102,7 @@ struct ArgsB {
 // the dpre image ring shared by the two roles
 struct RingB {
   int debug;        // FSNERF_DEBUG_FLAGS (tuning experiments only)
+  int stagger_ns;   // start of dgrad CTA b is delayed by stagger_ns * b / n_d
   uint8_t* base;    // [n_d][depth] slots of kImgSlotBytes
   uint32_t* prod;   // [n_d]
   uint32_t* cons;   // [n_d][depth]
@@ -113,22 +117,26 @@ constexpr int kSlabBytes = kSlabRows * 128;       // 8 KB per 64-feature chunk
 // A stage holds one 64-sample slab of the job's operands: (a_chunks + b_chunks) x 8 KB, so the
 // small jobs (encoding parts, branch) get a deeper ring out of the same 192 KB: their per-tile
 // work is a few hundred cycles and only tiles in flight hide the load latency.
-constexpr int kWRingBytes = 24 * kSlabBytes;      // 192 KB: 3 stages of a [256 x 256] job
+constexpr int kWRingBytes = 24 * kSlabBytes + 3 * 2048;  // 3 stages of a [256 x 256] job (+ its out / d_out rows)
 constexpr int kWMaxStages = 8;
 constexpr int kWSmemBars = kWRingBytes;            // full[8], empty[8], acc_full, TMEM slot, queue counters
 constexpr int kWQueue = 64;                        // tile queue entries (scout -> issuers / releaser)
 constexpr int kWSmemQueue = kWSmemBars + 256;
-constexpr int kWSmemTotal = kWSmemQueue + kWQueue * 4;
+constexpr int kWSmemTotal = kWSmemQueue + kWQueue * 4 + 64;  // + per-stage issue clocks (stats)
 constexpr int kScoutSlots = 5;                     // producers polled per scout lane (32 * 5 >= 148)
 constexpr int kMaxJobs = kMaxGemm + 4;
 
 struct WgradJob {
   int a_img, a_chunks;  // dpre image index in the ring sequence, N_out / 64
   int b_off, b_chunks;  // input image (stash record), K_in(part) / 64
+  int c_off, c_chunks;  // one more stash image staged for the side warps only (rgb head input), 0: none
   int w_off, ld, col0, ncols, nrows;
   int cta_begin, n_split;
   int cons_inc;         // what this reader adds to cons[] per image (2 / readers of the image)
+  int bias_off;         // >= 0: this job also sums the dpre columns into grads[bias_off ...]
+  int head;             // 1: sigma head from the B slabs (last hidden layer's output); 2: rgb head from the C slabs
 };
+constexpr int kSideWarp0 = 7, kSideWarps = 8;  // wgrad role: warps 7..14
 struct WgradPlan {
   int n_jobs, n_ctas;
   WgradJob job[kMaxJobs];
@@ -210,8 +218,9 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
   const uint32_t bar_img_done = sbase + BarsB::img_done;
   const uint32_t tmem_slot = sbase + BarsB::tmem_slot;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + BarsB::tmem_slot);
-  float* bias_acc = reinterpret_cast<float*>(smem + SmemB::bias);
   const float* heads = reinterpret_cast<const float*>(smem + SmemB::heads);
+  float* bias_acc = reinterpret_cast<float*>(smem + SmemB::bias);
+  const bool bias_here = (ring.debug & 8) == 0;  // FSNERF_DEBUG_FLAGS & 8: bias sums on the wgrad side warps instead (measured slower: 4.25 vs 3.42 ms)
   const int64_t n_tiles = (args.n_samples + kTileM - 1) / kTileM;
   const int64_t tile0 = blockIdx.x, tstride = ring.n_d;
   long long* stats = args.trace ? args.trace + kStatBase + 8 * blockIdx.x : nullptr;
@@ -243,6 +252,17 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
     const float* __restrict__ small = reinterpret_cast<const float*>(args.packed + prog.small_off);
     for (int i = threadIdx.x; i < 640; i += kThreadsB)
       reinterpret_cast<float*>(smem + SmemB::heads)[i] = __ldg(small + kSmallSigmaW + i);
+  }
+  // The dgrad CTAs start staggered over ~one tile period: in lock step, every wgrad CTA would be
+  // handed the same image of all its producers at once and drain the burst while they wait.
+  if (threadIdx.x == 0 && ring.stagger_ns > 0) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    const unsigned long long wait = (unsigned long long)ring.stagger_ns * blockIdx.x / (unsigned)ring.n_d;
+    do {
+      __nanosleep(200);
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    } while (t - t0 < wait);
   }
   tc_fence_before();
   __syncthreads();
@@ -276,8 +296,8 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
   } else if (warp >= kWarpRed0) {
     // ------------------------------------------------ store warps: ring images + bias gradients
     // one warp per lane quarter.  Per staged slab (32 rows x 64 features of one chunk): copy it
-    // into the current ring image, sum its 32 rows (lane l owns features 2l, 2l+1:
-    // conflict-free 4 B reads) into the bias-gradient accumulators, and free the buffer.
+    // into the current ring image and free the buffer (the bias gradients = column sums of these
+    // images are taken by the wgrad CTAs, which have every image in shared memory anyway).
     const int quarter = warp - kWarpRed0;
     const uint32_t stage_base = sbase + SmemB::staging + quarter * (kStageBufsB * kSlabBytesB);
     uint8_t* my_ring = ring.base + (size_t)blockIdx.x * ring.depth * kImgSlotBytes;
@@ -321,18 +341,20 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
 #pragma unroll
             for (int k = 0; k < 8; ++k) dst[k * 32 + lane] = t[k];
           }
-          float s0 = 0.f, s1 = 0.f;
-#pragma unroll 8
-          for (int r = 0; r < 32; ++r) {
-            uint32_t w;
-            asm volatile("ld.shared.b32 %0, [%1];"
-                         : "=r"(w)
-                         : "r"(buf + r * 128 + ((((uint32_t)lane >> 2) ^ (uint32_t)(r & 7)) << 4) + ((lane & 3) << 2)));
-            s0 += bf16_lo(w);
-            s1 += bf16_hi(w);
+          if (bias_here) {
+            float s0 = 0.f, s1 = 0.f, c0 = 0.f, c1 = 0.f;
+            const uint8_t* a = smem + SmemB::staging + quarter * (kStageBufsB * kSlabBytesB) + b * kSlabBytesB + ((lane & 3) << 2);
+            const uint32_t unit = (uint32_t)lane >> 2;
+#pragma unroll
+            for (int r = 0; r < 32; r += 2) {
+              const uint32_t w0 = *reinterpret_cast<const uint32_t*>(a + r * 128 + ((unit ^ (uint32_t)(r & 7)) << 4));
+              const uint32_t w1 = *reinterpret_cast<const uint32_t*>(a + (r + 1) * 128 + ((unit ^ (uint32_t)((r + 1) & 7)) << 4));
+              s0 += bf16_lo(w0); s1 += bf16_hi(w0);
+              c0 += bf16_lo(w1); c1 += bf16_hi(w1);
+            }
+            atomicAdd(bias_acc + layer * 256 + 64 * c + 2 * lane, s0 + c0);
+            atomicAdd(bias_acc + layer * 256 + 64 * c + 2 * lane + 1, s1 + c1);
           }
-          atomicAdd(bias_acc + layer * 256 + 64 * c + 2 * lane, s0);
-          atomicAdd(bias_acc + layer * 256 + 64 * c + 2 * lane + 1, s1);
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_slab_free + 8 * (quarter * kStageBufsB + b));
         }
@@ -489,12 +511,12 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
   __syncthreads();
   if (stats && threadIdx.x == 0) stats[0] = clock64() - t_begin;
   if (warp == kWarpMmaB) tmem_dealloc(tmem_base, 512);
-  // bias gradients of this CTA -> global
-  for (int g = 0; g < prog.n_gemm; ++g) {
-    const int ncols = prog.layer[g].n_halves * 128;
-    if ((int)threadIdx.x < ncols)
-      atomicAdd(args.grads + prog.layer[g].bias_off + threadIdx.x, bias_acc[g * 256 + threadIdx.x]);
-  }
+  if (bias_here)  // bias gradients of this CTA -> global
+    for (int g = 0; g < prog.n_gemm; ++g) {
+      const int ncols = prog.layer[g].n_halves * 128;
+      if ((int)threadIdx.x < ncols)
+        atomicAdd(args.grads + prog.layer[g].bias_off + threadIdx.x, bias_acc[g * 256 + threadIdx.x]);
+    }
 }
 
 // =========================================================================== wgrad role
@@ -530,12 +552,18 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
   }
   long long* stats = args.trace ? args.trace + kStatBase + 8 * blockIdx.x : nullptr;
   const long long t_begin = stats ? clock64() : 0;
-  const uint32_t stage_bytes = (uint32_t)(J.a_chunks + J.b_chunks) * kSlabBytes;
+  // head jobs also stage the slab's rows of out / d_out (fp32 [P,4]): 1 KB each behind the operand chunks
+  const uint32_t aux_off = (uint32_t)(J.a_chunks + J.b_chunks + J.c_chunks) * kSlabBytes;
+  const uint32_t stage_bytes = aux_off + (J.head ? 2048u : 0u);
+  const bool side = J.bias_off >= 0 || J.head != 0;
+  // tile of the slab held by each stage (written by issuing thread 0 before it arms the barrier)
+  volatile uint32_t* stage_tile = reinterpret_cast<volatile uint32_t*>(smem + kWSmemBars + 176);
+  volatile long long* issue_clk = reinterpret_cast<volatile long long*>(smem + kWSmemQueue + kWQueue * 4);  // stats only
   const uint32_t n_stages = (kWRingBytes / stage_bytes) < (uint32_t)kWMaxStages ? (kWRingBytes / stage_bytes) : (uint32_t)kWMaxStages;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWMaxStages; ++s) {
       mbar_init(bar_full + 8 * s, 8);   // eight issuing threads (two lanes of each of the four producer warps)
-      mbar_init(bar_empty + 8 * s, 2);  // the MMAs that read the stage (commit) + the releaser warp
+      mbar_init(bar_empty + 8 * s, side ? 2 + kSideWarps : 2);  // MMA commit + releaser (+ side warps)
     }
     mbar_init(bar_acc_full, 1);
     *ready_upto = 0;
@@ -559,13 +587,15 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
       // each: 64 rows of one chunk image) are spread over eight issuing threads, each arming
       // the stage barrier for its own bytes
       const int pw = (warp - 2) * 2 + lane;  // issuing thread index (lanes 0 and 1 issue)
-      const int n_cp = J.a_chunks + J.b_chunks;
+      const int n_cp = J.a_chunks + J.b_chunks + J.c_chunks;
       uint32_t cnt = 0;
       StatClock pc{0, stats != nullptr && warp == 2 && lane == 0};
       long long st_ready = 0, st_empty = 0;
       for (int64_t n = 0; n < n_my; ++n) {
         const uint8_t* a_img = nullptr;
         const uint8_t* b_img = nullptr;
+        const uint8_t* c_img = nullptr;
+        uint32_t tile_id = 0;
         pc.start();
         if (lane < 2) {  // the n-th tile the scout found published
           uint32_t spins = 0;
@@ -580,6 +610,8 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
           const uint32_t q = (uint32_t)(tile / ring.n_d) * (uint32_t)ring.n_img + (uint32_t)J.a_img;
           a_img = ring.base + ((size_t)b * ring.depth + q % (uint32_t)ring.depth) * kImgSlotBytes;
           b_img = args.stash + (size_t)tile * prog.stash_tile_bytes + J.b_off;
+          c_img = args.stash + (size_t)tile * prog.stash_tile_bytes + J.c_off;
+          tile_id = (uint32_t)tile;
           if (b == 0 && pw == 0 && J.cons_inc == 2) evt(args.trace, EVT_ISSUE, q);
         }
         pc.stop(st_ready);
@@ -592,20 +624,133 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
             const uint32_t sa = sbase + stage * stage_bytes, sb = sa + (uint32_t)J.a_chunks * kSlabBytes;
             int mine = 0;
             for (int c = pw; c < n_cp; c += 8) ++mine;
-            mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)mine * kSlabBytes);
+            if (pw == 0) {
+              stage_tile[stage] = tile_id;  // ordered before the arrive below (release)
+              if (stats) issue_clk[stage] = clock64();
+            }
+            uint32_t aux_bytes = 0;
+            const int64_t p0 = (int64_t)tile_id * kTileM + slab * kSlabRows;
+            if (J.head && pw == 7 && p0 < args.n_samples)
+              aux_bytes = (uint32_t)((args.n_samples - p0 < kSlabRows) ? (args.n_samples - p0) : kSlabRows) * 16u;
+            mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)mine * kSlabBytes + (J.head == 2 ? 2u : 1u) * aux_bytes);
+            if (aux_bytes) {
+              bulk_g2s(sa + aux_off + 1024, args.d_out + 4 * p0, aux_bytes, bar_full + 8 * stage);
+              if (J.head == 2) bulk_g2s(sa + aux_off, args.out + 4 * p0, aux_bytes, bar_full + 8 * stage);
+            }
             for (int c = pw; c < n_cp; c += 8) {
               if (c < J.a_chunks)
                 bulk_g2s(sa + c * kSlabBytes, a_img + c * kChunkBytes + slab * kSlabBytes, kSlabBytes,
                          bar_full + 8 * stage);
-              else
+              else if (c < J.a_chunks + J.b_chunks)
                 bulk_g2s(sb + (c - J.a_chunks) * kSlabBytes, b_img + (c - J.a_chunks) * kChunkBytes + slab * kSlabBytes,
                          kSlabBytes, bar_full + 8 * stage);
+              else
+                bulk_g2s(sb + (c - J.a_chunks) * kSlabBytes,
+                         c_img + (c - J.a_chunks - J.b_chunks) * kChunkBytes + slab * kSlabBytes, kSlabBytes,
+                         bar_full + 8 * stage);
             }
           }
           __syncwarp();
         }
       }
       if (pc.on) { stats[1] = st_ready; stats[2] = st_empty; }
+    } else if (warp >= kSideWarp0 && warp < kSideWarp0 + kSideWarps && side) {
+      // ------------------------------------------------ side warps (CUDA cores)
+      // Every slab of the job is in shared memory for at least the duration of its MMAs.  Warp sw
+      // takes chunk (sw & 3) and rows 32 * (sw >> 2) .. +32 of the 64-row slab; lane l owns the
+      // feature pair (2l, 2l+1) of that chunk (conflict-free 4 B reads of the SW128 rows).
+      const int sw = warp - kSideWarp0;
+      const int ch = sw & 3, r0 = (sw >> 2) * 32;
+      const uint32_t lane_off = (uint32_t)(lane & 3) << 2;
+      const uint32_t unit = (uint32_t)lane >> 2;
+      float b0 = 0.f, b1 = 0.f;                        // bias gradient (column sums of dpre)
+      float s0 = 0.f, s1 = 0.f, sb_sum = 0.f;          // sigma head
+      float rg[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}}, rb[3] = {0.f, 0.f, 0.f};  // rgb head
+      // rgb head: the C image is 128 wide (2 chunks): warp sw takes chunk (sw & 1), rows 16 * (sw >> 1) .. +16
+      const int ch2 = sw & 1, r2 = (sw >> 1) * 16;
+      uint32_t cnt = 0;
+      StatClock xc{0, stats != nullptr && sw == 0 && lane == 0};
+      long long st_busy = 0;
+      for (int64_t n = 0; n < n_my; ++n) {
+        for (int slab = 0; slab < kTileM / kSlabRows; ++slab, ++cnt) {
+          const uint32_t stage = cnt % n_stages, phase = (cnt / n_stages) & 1;
+          mbar_wait(bar_full + 8 * stage, phase);
+          xc.start();
+          const int64_t p0 = (int64_t)stage_tile[stage] * kTileM + slab * kSlabRows;
+          // plain loads (the barrier wait above is the compiler fence): a volatile asm per load
+          // would serialise the loop on the 29-cycle shared-memory latency
+          const uint8_t* st = smem + stage * stage_bytes;
+          const int64_t n_valid = args.n_samples - p0;  // rows of this slab that are real samples
+          if (J.bias_off >= 0 && ch < J.a_chunks) {
+            const uint8_t* a = st + ch * kSlabBytes + lane_off + r0 * 128;
+            float c0 = 0.f, c1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const uint32_t w0 = *reinterpret_cast<const uint32_t*>(a + i * 128 + ((unit ^ (uint32_t)(i & 7)) << 4));
+              const uint32_t w1 = *reinterpret_cast<const uint32_t*>(a + (i + 1) * 128 + ((unit ^ (uint32_t)((i + 1) & 7)) << 4));
+              b0 += bf16_lo(w0); b1 += bf16_hi(w0);
+              c0 += bf16_lo(w1); c1 += bf16_hi(w1);
+            }
+            b0 += c0; b1 += c1;
+          }
+          if (J.head == 1) {  // d(sigma weight)[k] += dsigma[s] * h[s][k]
+            const uint8_t* hrow = st + (J.a_chunks + ch) * kSlabBytes + lane_off + r0 * 128;
+            const uint8_t* drow = st + aux_off + 1024 + r0 * 16 + 12;
+            float c0 = 0.f, c1 = 0.f, cs = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float d0 = (r0 + i < n_valid) ? *reinterpret_cast<const float*>(drow + i * 16) : 0.f;
+              const float d1 = (r0 + i + 1 < n_valid) ? *reinterpret_cast<const float*>(drow + (i + 1) * 16) : 0.f;
+              const uint32_t w0 = *reinterpret_cast<const uint32_t*>(hrow + i * 128 + ((unit ^ (uint32_t)(i & 7)) << 4));
+              const uint32_t w1 = *reinterpret_cast<const uint32_t*>(hrow + (i + 1) * 128 + ((unit ^ (uint32_t)((i + 1) & 7)) << 4));
+              s0 = fmaf(d0, bf16_lo(w0), s0); s1 = fmaf(d0, bf16_hi(w0), s1);
+              c0 = fmaf(d1, bf16_lo(w1), c0); c1 = fmaf(d1, bf16_hi(w1), c1);
+              cs += d0 + d1;
+            }
+            s0 += c0; s1 += c1;
+            if (ch == 0) sb_sum += cs;  // every lane of the two chunk-0 warps holds the same sum
+          } else if (J.head == 2) {  // d(rgb weight)[c][k] += dz[s][c] * hb[s][k]
+            const uint8_t* xrow = st + (J.a_chunks + J.b_chunks + ch2) * kSlabBytes + lane_off + r2 * 128;
+            const uint8_t* orow = st + aux_off + r2 * 16;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float4 o4 = *reinterpret_cast<const float4*>(orow + i * 16);
+              const float4 g4 = *reinterpret_cast<const float4*>(orow + 1024 + i * 16);
+              const bool ok = r2 + i < n_valid;
+              const float dz0 = ok ? g4.x * o4.x * (1.0f - o4.x) : 0.f;
+              const float dz1 = ok ? g4.y * o4.y * (1.0f - o4.y) : 0.f;
+              const float dz2 = ok ? g4.z * o4.z * (1.0f - o4.z) : 0.f;
+              const uint32_t w = *reinterpret_cast<const uint32_t*>(xrow + i * 128 + ((unit ^ (uint32_t)((r2 + i) & 7)) << 4));
+              const float x0 = bf16_lo(w), x1 = bf16_hi(w);
+              rg[0][0] = fmaf(dz0, x0, rg[0][0]); rg[0][1] = fmaf(dz0, x1, rg[0][1]);
+              rg[1][0] = fmaf(dz1, x0, rg[1][0]); rg[1][1] = fmaf(dz1, x1, rg[1][1]);
+              rg[2][0] = fmaf(dz2, x0, rg[2][0]); rg[2][1] = fmaf(dz2, x1, rg[2][1]);
+              if (ch2 == 0) { rb[0] += dz0; rb[1] += dz1; rb[2] += dz2; }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
+          xc.stop(st_busy);
+        }
+      }
+      if (xc.on) stats[7] = st_busy;
+      // one atomic per feature and warp at the very end
+      if (J.bias_off >= 0 && ch < J.a_chunks) {
+        atomicAdd(args.grads + J.bias_off + 64 * ch + 2 * lane, b0);
+        atomicAdd(args.grads + J.bias_off + 64 * ch + 2 * lane + 1, b1);
+      }
+      if (J.head == 1) {
+        atomicAdd(args.grads + prog.sigma_w_off + 64 * ch + 2 * lane, s0);
+        atomicAdd(args.grads + prog.sigma_w_off + 64 * ch + 2 * lane + 1, s1);
+        if (ch == 0 && lane == 0) atomicAdd(args.grads + prog.sigma_b_off, sb_sum);
+      } else if (J.head == 2) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          atomicAdd(args.grads + prog.rgb_w_off + c * 128 + 64 * ch2 + 2 * lane, rg[c][0]);
+          atomicAdd(args.grads + prog.rgb_w_off + c * 128 + 64 * ch2 + 2 * lane + 1, rg[c][1]);
+          if (ch2 == 0 && lane == 0) atomicAdd(args.grads + prog.rgb_b_off + c, rb[c]);
+        }
+      }
     } else if (warp == 6) {
       // releaser: once the last slab of a tile has landed, the whole dpre image is in shared
       // memory and its ring slot goes back to the dgrad CTA.  It also arrives on the stage's
@@ -688,13 +833,14 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
       const uint32_t idesc = umma_idesc_bf16(128, J.b_chunks * 64, 1, 1);
       uint32_t cnt = 0;
       StatClock mc{0, stats != nullptr && lane == 0};
-      long long st_full = 0;
+      long long st_full = 0, st_lat = 0;
       for (int64_t n = 0; n < n_my; ++n) {
         for (int slab = 0; slab < kTileM / kSlabRows; ++slab, ++cnt) {
           const uint32_t stage = cnt % n_stages, phase = (cnt / n_stages) & 1;
           mc.start();
           mbar_wait(bar_full + 8 * stage, phase);
           mc.stop(st_full);
+          if (mc.on) st_lat += clock64() - issue_clk[stage];
           tc_fence_after();
           if (lane == 0) {
             const uint32_t sa = sbase + stage * stage_bytes, sb = sa + (uint32_t)J.a_chunks * kSlabBytes;
@@ -714,7 +860,7 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
       }
       if (lane == 0) umma_commit(bar_acc_full);
       __syncwarp();
-      if (mc.on) { stats[3] = st_full; stats[4] = n_my; stats[6] = j; }
+      if (mc.on) { stats[3] = st_full; stats[4] = n_my; stats[6] = j; stats[5] = st_lat; }
     }
     if (warp >= 2 && warp < 6) {
       const int quarter = warp & 3;
@@ -870,8 +1016,8 @@ mlp_heads_wgrad_kernel(const __grid_constant__ HeadsArgs a) {
 }
 
 // ------------------------------------------------------------------ host-side plan
-constexpr int kFlagBytes = 16384;  // prod [148] + cons [148][kMaxRingDepth] uint32, padded
-constexpr int kMaxRingDepth = 16;
+constexpr int kFlagBytes = 32768;  // prod [148] + cons [148][kMaxRingDepth] uint32, padded
+constexpr int kMaxRingDepth = 32;
 
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
@@ -888,6 +1034,13 @@ int job_overhead_cycles() {
   static int v = -1;
   if (v < 0) v = env_int("FSNERF_BWD_JOB_OVERHEAD", 2000);
   return v;
+}
+// Measured: the two heads are ~4800 CUDA-core cycles per tile (issue bound), which the branch /
+// connection jobs cannot absorb without several more CTAs; their own small kernel is faster.
+bool fuse_heads() {
+  static int v = -1;
+  if (v < 0) v = env_int("FSNERF_BWD_FUSE_HEADS", 0);
+  return v != 0;
 }
 int ring_depth_for(int n_img) {
   static int v = -1;
@@ -982,12 +1135,14 @@ extern "C" int fsnerf_mlp_backward(const fsnerf_net_cfg* cfg, const float* param
   ha.g_sigma_w = grads + P.sigma_w_off; ha.g_sigma_b = grads + P.sigma_b_off;
   ha.g_rgb_w = grads + P.rgb_w_off; ha.g_rgb_b = grads + P.rgb_b_off;
   const int hgrid = (int)(n_tiles < 6 * kNumSMs ? n_tiles : 6 * kNumSMs);
-  {
-    FsProfScope prof_("mlp_heads_wgrad", stream);
-    mlp_heads_wgrad_kernel<<<hgrid, 256, 0, st>>>(ha);
+  if (!fuse_heads()) {
+    {
+      FsProfScope prof_("mlp_heads_wgrad", stream);
+      mlp_heads_wgrad_kernel<<<hgrid, 256, 0, st>>>(ha);
+    }
+    rc = fsnerf_check_launch("mlp_backward(heads)");
+    if (rc != FSNERF_OK) return rc;
   }
-  rc = fsnerf_check_launch("mlp_backward(heads)");
-  if (rc != FSNERF_OK) return rc;
 
   // ---- dgrad plan + issue table
   PlanB PL;
@@ -1052,6 +1207,15 @@ extern "C" int fsnerf_mlp_backward(const fsnerf_net_cfg* cfg, const float* param
       J.a_img = P.n_gemm - 1 - g; J.a_chunks = a_chunks;
       J.w_off = L.w_off; J.ld = L.ld; J.nrows = L.n_halves * 128;
       J.cons_inc = 2 / readers[g];
+      J.c_off = 0; J.c_chunks = 0; J.head = 0;
+      // the layer's bias gradient rides on its lighter job; the heads on the jobs that stage their inputs
+      J.bias_off = ((part == 1 || !L.use_aux) && (env_int("FSNERF_DEBUG_FLAGS", 0) & 8)) ? L.bias_off : -1;
+      if (fuse_heads()) {  // FSNERF_BWD_FUSE_HEADS=1: the heads on the side warps instead of their own kernel
+        if (L.epi == EPI_CONN && part == 0) J.head = 1;  // B = the last hidden layer's output
+        if (L.epi == EPI_BRANCH && part == 1) {          // C = the branch layer's own output image
+          J.head = 2; J.c_off = L.stash_off; J.c_chunks = L.n_halves * 2;
+        }
+      }
       if (part == 0) {
         J.b_off = P.layer[g - 1].stash_off; J.b_chunks = L.n_act_chunks;
         J.col0 = 0; J.ncols = L.n_act_chunks * 64;
@@ -1109,6 +1273,7 @@ extern "C" int fsnerf_mlp_backward(const fsnerf_net_cfg* cfg, const float* param
   RG.depth = ring_depth_for(P.n_gemm);
   RG.n_img = P.n_gemm;
   RG.debug = env_int("FSNERF_DEBUG_FLAGS", 0);
+  RG.stagger_ns = (n_tiles >= 4 * (int64_t)sp.n_d) ? env_int("FSNERF_BWD_STAGGER_NS", 30000) : 0;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   RG.prod = reinterpret_cast<uint32_t*>(ws);
   RG.cons = RG.prod + 256;

@@ -34,12 +34,12 @@ for k, name in [(0, "total"), (1, "store warp: ring slot (cons) wait"), (2, "sto
                 (4, "epilogue: accumulator wait")]:
     c = dg[:, k]
     print(f"  {name:40s} {c.mean():9.1f} [{c.min():9.1f} .. {c.max():9.1f}]")
-print(f"wgrad CTAs ({n_w}), per job: CTAs, tiles/CTA, total kcyc, producer ready-wait, producer empty-wait, MMA full-wait")
+print(f"wgrad CTAs ({n_w}), per job: CTAs, tiles/CTA, total kcyc, producer ready-wait, producer empty-wait, MMA full-wait, cycles issue->landed per stage")
 for j in sorted(set(int(x) for x in (wg[:, 6] * 1e3).round().tolist())):
     m = (wg[:, 6] * 1e3).round() == j
     r = wg[m]
     print(f"  job {j:2d}: {int(m.sum()):3d} {r[:, 4].mean() * 1e3:7.0f} {r[:, 0].mean():9.1f} {r[:, 1].mean():9.1f} "
-          f"{r[:, 2].mean():9.1f} {r[:, 3].mean():9.1f}")
+          f"{r[:, 2].mean():9.1f} {r[:, 3].mean():9.1f} {(r[:, 5] / (2 * r[:, 4])).mean():9.0f} side-busy {r[:, 7].mean():9.1f}")
 
 # life of the first images of dgrad CTA 0 (global timer, us relative to the first event)
 e = trace.cpu()[4096:4096 + 7 * 256].view(7, 256).double()
