@@ -77,8 +77,9 @@ struct BarsB {
   static constexpr int slab_free = slab_full + 8 * 4 * kStageBufsB;
   static constexpr int img_done = slab_free + 8 * 4 * kStageBufsB;   // [kImgBars]
   static constexpr int tmem_slot = img_done + 8 * kImgBars;
+  static constexpr int feed = tmem_slot + 8;   // int[5]: tile feed (mlp_issue.cuh: TileSeq)
 };
-static_assert(BarsB::tmem_slot + 8 <= SmemB::total, "barrier block overflows");
+static_assert(BarsB::feed + 32 <= SmemB::total, "barrier block overflows");
 
 struct StepB {
   int target;      // layer whose d(pre-activation) this step produces
@@ -102,7 +103,9 @@ struct ArgsB {
 // the dpre image ring shared by the two roles
 struct RingB {
   int debug;        // FSNERF_DEBUG_FLAGS (tuning experiments only)
-  int stagger_ns;   // start of dgrad CTA b is delayed by stagger_ns * b / n_d
+  uint32_t* tile_ctr;  // next unclaimed tile (dynamic scheduling of the dgrad CTAs)
+  int32_t* tile_of;    // [n_d][row_cap]: tile claimed by dgrad CTA b for its iteration i, -1 past its last
+  int row_cap;
   uint8_t* base;    // [n_d][depth] slots of kImgSlotBytes
   uint32_t* prod;   // [n_d]
   uint32_t* cons;   // [n_d][depth]
@@ -122,7 +125,8 @@ constexpr int kWMaxStages = 8;
 constexpr int kWSmemBars = kWRingBytes;            // full[8], empty[8], acc_full, TMEM slot, queue counters
 constexpr int kWQueue = 64;                        // tile queue entries (scout -> issuers / releaser)
 constexpr int kWSmemQueue = kWSmemBars + 256;
-constexpr int kWSmemTotal = kWSmemQueue + kWQueue * 4 + 64;  // + per-stage issue clocks (stats)
+constexpr int kWSmemFlush = kWSmemQueue + kWQueue * 8 + 64;  // two words per queue entry; + per-stage issue clocks (stats)
+constexpr int kWSmemTotal = kWSmemFlush + 4 * (32 * 33 * 4);  // + transposition scratch of the four flushing warps
 constexpr int kScoutSlots = 5;                     // producers polled per scout lane (32 * 5 >= 148)
 constexpr int kMaxJobs = kMaxGemm + 4;
 
@@ -222,7 +226,12 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
   float* bias_acc = reinterpret_cast<float*>(smem + SmemB::bias);
   const bool bias_here = (ring.debug & 8) == 0;  // FSNERF_DEBUG_FLAGS & 8: bias sums on the wgrad side warps instead (measured slower: 4.25 vs 3.42 ms)
   const int64_t n_tiles = (args.n_samples + kTileM - 1) / kTileM;
-  const int64_t tile0 = blockIdx.x, tstride = ring.n_d;
+  // Tiles are claimed from a global counter (the ring manager keeps the feed two tiles ahead):
+  // the dgrad CTAs do not run at the same speed (they are throttled by different wgrad CTAs and
+  // sit at different distances from the L2 slices they stream from), a static split ends with
+  // the slowest one.
+  volatile int* feed = reinterpret_cast<volatile int*>(smem + BarsB::feed);
+  const TileSeq seq{feed, 0, 0, n_tiles};
   long long* stats = args.trace ? args.trace + kStatBase + 8 * blockIdx.x : nullptr;
   const long long t_begin = stats ? clock64() : 0;
 
@@ -241,6 +250,7 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
       mbar_init(bar_slab_free + 8 * i, 1);  // the quarter's store warp
     }
     for (int i = 0; i < kImgBars; ++i) mbar_init(bar_img_done + 8 * i, kRedWarpsB);
+    feed[0] = 0;
     fence_barrier_init();
   }
   if (warp == kWarpMmaB) {
@@ -252,17 +262,6 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
     const float* __restrict__ small = reinterpret_cast<const float*>(args.packed + prog.small_off);
     for (int i = threadIdx.x; i < 640; i += kThreadsB)
       reinterpret_cast<float*>(smem + SmemB::heads)[i] = __ldg(small + kSmallSigmaW + i);
-  }
-  // The dgrad CTAs start staggered over ~one tile period: in lock step, every wgrad CTA would be
-  // handed the same image of all its producers at once and drain the burst while they wait.
-  if (threadIdx.x == 0 && ring.stagger_ns > 0) {
-    unsigned long long t0, t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
-    const unsigned long long wait = (unsigned long long)ring.stagger_ns * blockIdx.x / (unsigned)ring.n_d;
-    do {
-      __nanosleep(200);
-      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    } while (t - t0 < wait);
   }
   tc_fence_before();
   __syncthreads();
@@ -277,22 +276,46 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
     // stores at CTA scope; the fence below makes the publication cumulative at GPU scope.
     if (lane == 0) {
       uint32_t* my_prod = ring.prod + blockIdx.x;
+      int32_t* my_tiles = ring.tile_of + (size_t)blockIdx.x * ring.row_cap;
+      int n_claimed = 0;
+      bool dry = false;
+      auto claim_upto = [&](int want) {  // tiles of iterations < want are known
+        while (n_claimed < want) {
+          int t = -1;
+          if (!dry && n_claimed < ring.row_cap - 1) {
+            // (FSNERF_DEBUG_FLAGS & 16: the static split blockIdx, blockIdx + n_d, ... for A/B runs)
+            const int64_t c = (ring.debug & 16) ? (int64_t)blockIdx.x + (int64_t)n_claimed * ring.n_d
+                                                : (int64_t)atomicAdd(ring.tile_ctr, 1u);
+            if (c < n_tiles) t = (int)c;
+          }
+          if (t < 0) dry = true;
+          if (n_claimed < ring.row_cap) my_tiles[n_claimed] = t;  // read by the wgrad scouts after they acquire prod
+          feed[1 + (n_claimed & 3)] = t;
+          __threadfence_block();
+          feed[0] = ++n_claimed;
+        }
+      };
+      claim_upto(2);
       uint32_t q = 0;
-      for (int64_t tile = tile0; tile < n_tiles; tile += tstride)
+      for (int it = 0; feed[1 + (it & 3)] >= 0; ++it) {
+        claim_upto(it + 3);  // iteration it + 2: the weight producers / MMA issuers run up to ~1 tile ahead
         for (int k = 0; k < ring.n_img; ++k, ++q) {
           mbar_wait_relaxed(bar_img_done + 8 * (q % kImgBars), (q / kImgBars) & 1);
           if (blockIdx.x == 0) evt(args.trace, EVT_DONE, q);
           st_release_u32(my_prod, q + 1);  // release = fence.acq_rel.gpu + store
           if (blockIdx.x == 0) evt(args.trace, EVT_PUB, q);
         }
+      }
+      // end marker: the iteration after the last reads as published and its tile_of entry is -1
+      st_release_u32(my_prod, q + (uint32_t)ring.n_img);
     }
   } else if (warp == kWarpProdB) {
     IssueBars IB{bar_w_full, bar_w_empty, bar_token, sbase + SmemB::ring};
-    if (lane < kProdWarps) producer_loop_thread<kStagesB>(tab, IB, args.packed, n_tiles, lane, tile0, tstride);
+    if (lane < kProdWarps) producer_loop_thread<kStagesB>(tab, IB, args.packed, seq, lane);
   } else if (warp >= kWarpMmaB) {
     if (tmem_base != 0) __trap();
     IssueBars IB{bar_w_full, bar_w_empty, bar_token, sbase + SmemB::ring};
-    issuer_loop<kStagesB>(tab, IB, sbase, n_tiles, (uint32_t)(warp - kWarpMmaB), lane, args.trace, tile0, tstride);
+    issuer_loop<kStagesB>(tab, IB, sbase, seq, (uint32_t)(warp - kWarpMmaB), lane, args.trace);
   } else if (warp >= kWarpRed0) {
     // ------------------------------------------------ store warps: ring images + bias gradients
     // one warp per lane quarter.  Per staged slab (32 rows x 64 features of one chunk): copy it
@@ -307,7 +330,7 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
     uint32_t cons_seen = 0;  // the upcoming slot's counter, fetched (acquire) one image ahead by lane 0
     StatClock sc{0, stats != nullptr && quarter == 0 && lane == 0};
     long long st_cons = 0, st_slab = 0, st_pub = 0;
-    for (int64_t tile = tile0; tile < n_tiles; tile += tstride) {
+    for (uint32_t it = 0; seq.get(it) >= 0; ++it) {
       for (int s = -1; s < plan.n_steps; ++s, ++q) {
         const int layer = (s < 0) ? plan.g_branch : plan.step[s].target;
         const int nchunk = (s < 0) ? 2 : 4;
@@ -400,7 +423,7 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
       if (lane == 0) mbar_arrive(bar_slab_full + 8 * (quarter * kStageBufsB + b));  // release: stores visible
       ++n_staged;
     };
-    for (int64_t tile = tile0; tile < n_tiles; tile += tstride, ++titer) {
+    for (int64_t tile; (tile = seq.get(titer)) >= 0; ++titer) {
       const int64_t p = tile * kTileM + row;
       const bool valid = p < args.n_samples;
       const uint8_t* stash_tile = args.stash + (size_t)tile * prog.stash_tile_bytes;
@@ -545,11 +568,19 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
   // whatever order they are published: a consumer bound to a fixed tile order would stall on one
   // late producer while the others fill their rings and stall too.
   const int n_mine = (ring.n_d > part) ? (ring.n_d - part + J.n_split - 1) / J.n_split : 0;
-  int64_t n_my = 0;
-  for (int k = 0; k < n_mine; ++k) {
-    const int b = part + k * J.n_split;
-    if (n_tiles > b) n_my += (n_tiles - b + ring.n_d - 1) / ring.n_d;
-  }
+  // how many tiles that is is only known at the end (the dgrad CTAs claim tiles dynamically): the
+  // scout publishes the total once every producer has sent its end marker
+  volatile uint32_t* final_count = reinterpret_cast<volatile uint32_t*>(smem + kWSmemBars + 168);
+  auto have_tile = [&](uint32_t n) -> bool {  // false: no n-th tile, the CTA's list has ended
+    uint32_t spins = 0;
+    while (*ready_upto <= n) {
+      if (*final_count != 0xFFFFFFFFu) return n < *final_count;
+      __nanosleep(32);
+      if (++spins > (1u << 24)) { printf("fsnerf: wgrad scout timeout blk %d thr %d\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+    __threadfence_block();
+    return true;
+  };
   long long* stats = args.trace ? args.trace + kStatBase + 8 * blockIdx.x : nullptr;
   const long long t_begin = stats ? clock64() : 0;
   // head jobs also stage the slab's rows of out / d_out (fp32 [P,4]): 1 KB each behind the operand chunks
@@ -558,7 +589,7 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
   const bool side = J.bias_off >= 0 || J.head != 0;
   // tile of the slab held by each stage (written by issuing thread 0 before it arms the barrier)
   volatile uint32_t* stage_tile = reinterpret_cast<volatile uint32_t*>(smem + kWSmemBars + 176);
-  volatile long long* issue_clk = reinterpret_cast<volatile long long*>(smem + kWSmemQueue + kWQueue * 4);  // stats only
+  volatile long long* issue_clk = reinterpret_cast<volatile long long*>(smem + kWSmemQueue + kWQueue * 8);  // stats only
   const uint32_t n_stages = (kWRingBytes / stage_bytes) < (uint32_t)kWMaxStages ? (kWRingBytes / stage_bytes) : (uint32_t)kWMaxStages;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWMaxStages; ++s) {
@@ -568,6 +599,7 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
     mbar_init(bar_acc_full, 1);
     *ready_upto = 0;
     *released_upto = 0;
+    *final_count = (n_mine > 0) ? 0xFFFFFFFFu : 0u;
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -580,7 +612,7 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
   const uint32_t tmem_base = *tmem_slot_ptr;
   const int n_mh = J.a_chunks / 2;
 
-  if (n_my > 0) {
+  {
     if (warp >= 2 && warp < 6) {
       // four producer warps (the epilogue warps, idle during the main loop): bulk copies issued
       // by one thread do not overlap (tools/l2_bench.cu), so each stage's slab copies (8 KB
@@ -591,23 +623,19 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
       uint32_t cnt = 0;
       StatClock pc{0, stats != nullptr && warp == 2 && lane == 0};
       long long st_ready = 0, st_empty = 0;
-      for (int64_t n = 0; n < n_my; ++n) {
+      for (uint32_t n = 0;; ++n) {
         const uint8_t* a_img = nullptr;
         const uint8_t* b_img = nullptr;
         const uint8_t* c_img = nullptr;
         uint32_t tile_id = 0;
         pc.start();
+        if (!have_tile(n)) break;  // (every lane: the warp stays together)
         if (lane < 2) {  // the n-th tile the scout found published
-          uint32_t spins = 0;
-          while (*ready_upto <= (uint32_t)n) {
-            __nanosleep(32);
-            if (++spins > (1u << 24)) { printf("fsnerf: wgrad scout timeout blk %d\n", blockIdx.x); __trap(); }
-          }
-          __threadfence_block();
           fence_proxy_async_global();
-          const int64_t tile = queue[n % kWQueue];
-          const int b = (int)(tile % ring.n_d);
-          const uint32_t q = (uint32_t)(tile / ring.n_d) * (uint32_t)ring.n_img + (uint32_t)J.a_img;
+          const int64_t tile = queue[2 * (n % kWQueue)];
+          const uint32_t bi = queue[2 * (n % kWQueue) + 1];  // producer | its iteration << 8
+          const int b = (int)(bi & 255u);
+          const uint32_t q = (bi >> 8) * (uint32_t)ring.n_img + (uint32_t)J.a_img;
           a_img = ring.base + ((size_t)b * ring.depth + q % (uint32_t)ring.depth) * kImgSlotBytes;
           b_img = args.stash + (size_t)tile * prog.stash_tile_bytes + J.b_off;
           c_img = args.stash + (size_t)tile * prog.stash_tile_bytes + J.c_off;
@@ -671,7 +699,7 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
       uint32_t cnt = 0;
       StatClock xc{0, stats != nullptr && sw == 0 && lane == 0};
       long long st_busy = 0;
-      for (int64_t n = 0; n < n_my; ++n) {
+      for (uint32_t n = 0; have_tile(n); ++n) {
         for (int slab = 0; slab < kTileM / kSlabRows; ++slab, ++cnt) {
           const uint32_t stage = cnt % n_stages, phase = (cnt / n_stages) & 1;
           mbar_wait(bar_full + 8 * stage, phase);
@@ -757,14 +785,14 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
       // empty barrier so that it can never fall a barrier phase behind.
       if (lane == 0) {
         uint32_t cnt = 0;
-        for (int64_t n = 0; n < n_my; ++n) {
+        for (uint32_t n = 0; have_tile(n); ++n) {
           for (int slab = 0; slab < kTileM / kSlabRows; ++slab, ++cnt) {
             const uint32_t stage = cnt % n_stages, phase = (cnt / n_stages) & 1;
             mbar_wait_relaxed(bar_full + 8 * stage, phase);
             if (slab == kTileM / kSlabRows - 1) {
-              const int64_t tile = queue[n % kWQueue];
-              const int b = (int)(tile % ring.n_d);
-              const uint32_t q = (uint32_t)(tile / ring.n_d) * (uint32_t)ring.n_img + (uint32_t)J.a_img;
+              const uint32_t bi = queue[2 * (n % kWQueue) + 1];
+              const int b = (int)(bi & 255u);
+              const uint32_t q = (bi >> 8) * (uint32_t)ring.n_img + (uint32_t)J.a_img;
               red_relaxed_add_u32(ring.cons + (size_t)b * ring.depth + q % (uint32_t)ring.depth, (uint32_t)J.cons_inc);
               *released_upto = (uint32_t)(n + 1);
               if (b == 0 && J.cons_inc == 2) evt(args.trace, EVT_REL, q);
@@ -776,21 +804,27 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
     } else if (warp == 0) {
       // scout: every lane watches up to kScoutSlots of this CTA's producers and appends a tile to
       // the queue as soon as its image is published (at most one per producer per sweep)
-      uint32_t nxt[kScoutSlots];
+      uint32_t nxt[kScoutSlots];   // next iteration of each watched producer, 0xFFFFFFFF: it has ended
 #pragma unroll
-      for (int sl = 0; sl < kScoutSlots; ++sl) nxt[sl] = 0;
+      for (int sl = 0; sl < kScoutSlots; ++sl) nxt[sl] = (lane + 32 * sl < n_mine) ? 0u : 0xFFFFFFFFu;
       uint32_t enq = 0, idle = 0;
-      while (enq < (uint32_t)n_my) {
-        bool any = false;
+      for (;;) {
+        bool any = false, live = false;
 #pragma unroll
         for (int sl = 0; sl < kScoutSlots; ++sl) {
           const int k = lane + 32 * sl;
           const int b = part + k * J.n_split;
           bool flag = false;
-          if (k < n_mine && n_tiles > b && (int64_t)nxt[sl] < (n_tiles - b + ring.n_d - 1) / ring.n_d) {
+          int32_t t = -1;
+          if (nxt[sl] != 0xFFFFFFFFu) {
             const uint32_t need = nxt[sl] * (uint32_t)ring.n_img + (uint32_t)J.a_img + 1u;
-            flag = (int32_t)(ld_acquire_u32(ring.prod + b) - need) >= 0;
+            if ((int32_t)(ld_acquire_u32(ring.prod + b) - need) >= 0) {
+              t = ring.tile_of[(size_t)b * ring.row_cap + nxt[sl]];
+              if (t < 0) nxt[sl] = 0xFFFFFFFFu;  // end marker
+              else flag = true;
+            }
           }
+          live = live || nxt[sl] != 0xFFFFFFFFu;
           const uint32_t mask = __ballot_sync(0xffffffffu, flag);
           if (mask) {
             const uint32_t cntm = __popc(mask);
@@ -804,7 +838,8 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
             __syncwarp();
             if (flag) {
               const uint32_t pos = enq + __popc(mask & ((1u << lane) - 1u));
-              queue[pos % kWQueue] = (uint32_t)(b + (int64_t)nxt[sl] * ring.n_d);
+              queue[2 * (pos % kWQueue)] = (uint32_t)t;
+              queue[2 * (pos % kWQueue) + 1] = (uint32_t)b | (nxt[sl] << 8);
               if (b == 0) evt(args.trace, EVT_SCOUT, nxt[sl] * (uint32_t)ring.n_img + (uint32_t)J.a_img);
               ++nxt[sl];
             }
@@ -817,15 +852,20 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
             any = true;
           }
         }
+        if (!__any_sync(0xffffffffu, live)) break;
         if (any) {
           idle = 0;
         } else {
           __nanosleep(128);
           if (++idle > (1u << 22)) {
-            if (lane == 0) printf("fsnerf: wgrad scout found nothing to do for too long, blk %d enq %u of %lld\n", blockIdx.x, enq, (long long)n_my);
+            if (lane == 0) printf("fsnerf: wgrad scout found nothing to do for too long, blk %d enq %u\n", blockIdx.x, enq);
             __trap();
           }
         }
+      }
+      if (lane == 0) {
+        __threadfence_block();
+        *final_count = enq;
       }
     } else if (warp == 1) {
       // A = dpre^T (M = output features), B = X^T (N = input features); both MN-major:
@@ -834,7 +874,8 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
       uint32_t cnt = 0;
       StatClock mc{0, stats != nullptr && lane == 0};
       long long st_full = 0, st_lat = 0;
-      for (int64_t n = 0; n < n_my; ++n) {
+      uint32_t n_done = 0;
+      for (uint32_t n = 0; have_tile(n); ++n, ++n_done) {
         for (int slab = 0; slab < kTileM / kSlabRows; ++slab, ++cnt) {
           const uint32_t stage = cnt % n_stages, phase = (cnt / n_stages) & 1;
           mc.start();
@@ -860,23 +901,31 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
       }
       if (lane == 0) umma_commit(bar_acc_full);
       __syncwarp();
-      if (mc.on) { stats[3] = st_full; stats[4] = n_my; stats[6] = j; stats[5] = st_lat; }
+      if (mc.on) { stats[3] = st_full; stats[4] = n_done; stats[6] = j; stats[5] = st_lat; }
     }
-    if (warp >= 2 && warp < 6) {
+    if (warp >= 2 && warp < 6 && *final_count != 0) {
       const int quarter = warp & 3;
       mbar_wait(bar_acc_full, 0);
       tc_fence_after();
+      // The accumulator tile of a warp is [32 rows (lanes) x 32 columns (registers)]; a straight
+      // flush would issue atomics strided by a weight row (32 cache lines per instruction).  It is
+      // transposed through shared memory instead: lane = column, one line per atomic.
+      float* tr = reinterpret_cast<float*>(smem + kWSmemFlush + (warp - 2) * (32 * 33 * 4));
       for (int mh = 0; mh < n_mh; ++mh) {
-        const int r = mh * 128 + quarter * 32 + lane;
-        float* __restrict__ grow = args.grads + J.w_off + (size_t)r * J.ld + J.col0;
+        const int rbase = mh * 128 + quarter * 32;
         for (int c0 = 0; c0 < J.b_chunks * 64; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + mh * 256 + c0, v);
           tmem_ld_wait();
-          if (r < J.nrows) {
+          __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c0 + i < J.ncols) atomicAdd(grow + c0 + i, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) tr[lane * 33 + i] = __uint_as_float(v[i]);
+          __syncwarp();
+          if (c0 + lane < J.ncols) {
+            float* __restrict__ gcol = args.grads + J.w_off + J.col0 + c0 + lane;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr)
+              if (rbase + rr < J.nrows) atomicAdd(gcol + (size_t)(rbase + rr) * J.ld, tr[rr * 33 + lane]);
           }
         }
       }
@@ -894,10 +943,20 @@ mlp_bwd_fused_kernel(const __grid_constant__ MlpProgram prog, const __grid_const
                      const __grid_constant__ WgradPlan wplan, const __grid_constant__ RingB ring) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (args.trace && threadIdx.x == 0) {  // tuning aid: CTA life span on the global timer (ns)
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    args.trace[6144 + 2 * blockIdx.x] = (long long)t;
+  }
   if ((int)blockIdx.x < ring.n_d)
     dgrad_cta(smem, prog, plan, args, tab, ring);
   else
     wgrad_cta(smem, prog, args, wplan, ring);
+  if (args.trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    args.trace[6144 + 2 * blockIdx.x + 1] = (long long)t;
+  }
 }
 
 // =========================================================================== heads (SIMT)
@@ -1027,12 +1086,12 @@ int env_int(const char* name, int dflt) {
 // (FSNERF_BWD_RING_DEPTH): tuning knobs, read once
 int wgrad_ctas_wanted() {
   static int v = -1;
-  if (v < 0) v = env_int("FSNERF_BWD_WGRAD_CTAS", 50);
+  if (v < 0) v = env_int("FSNERF_BWD_WGRAD_CTAS", 58);
   return v;
 }
 int job_overhead_cycles() {
   static int v = -1;
-  if (v < 0) v = env_int("FSNERF_BWD_JOB_OVERHEAD", 2000);
+  if (v < 0) v = env_int("FSNERF_BWD_JOB_OVERHEAD", 3000);
   return v;
 }
 // Measured: the two heads are ~4800 CUDA-core cycles per tile (issue bound), which the branch /
@@ -1041,6 +1100,11 @@ bool fuse_heads() {
   static int v = -1;
   if (v < 0) v = env_int("FSNERF_BWD_FUSE_HEADS", 0);
   return v != 0;
+}
+// tile_of rows: a dgrad CTA may claim up to 4x its even share (then it stops claiming)
+int tile_row_cap(int64_t n_tiles, int n_d) { return (int)(4 * ((n_tiles + n_d - 1) / n_d) + 8); }
+int64_t tile_table_bytes(int64_t n_tiles, int n_d) {
+  return (((int64_t)n_d * tile_row_cap(n_tiles, n_d) * 4) + 1023) & ~(int64_t)1023;
 }
 int ring_depth_for(int n_img) {
   static int v = -1;
@@ -1086,7 +1150,8 @@ extern "C" int64_t fsnerf_mlp_bwd_workspace_bytes(const fsnerf_net_cfg* cfg, int
   if (n_samples <= 0) return kFlagBytes;
   const int64_t n_tiles = (n_samples + kTileM - 1) / kTileM;
   const SplitB sp = split_roles(count_jobs(P), n_tiles);
-  return (int64_t)kFlagBytes + (int64_t)sp.n_d * ring_depth_for(P.n_gemm) * kImgSlotBytes;
+  return (int64_t)kFlagBytes + tile_table_bytes(n_tiles, sp.n_d) +
+         (int64_t)sp.n_d * ring_depth_for(P.n_gemm) * kImgSlotBytes;
 }
 
 extern "C" int fsnerf_mlp_backward(const fsnerf_net_cfg* cfg, const float* params,
@@ -1273,11 +1338,13 @@ extern "C" int fsnerf_mlp_backward(const fsnerf_net_cfg* cfg, const float* param
   RG.depth = ring_depth_for(P.n_gemm);
   RG.n_img = P.n_gemm;
   RG.debug = env_int("FSNERF_DEBUG_FLAGS", 0);
-  RG.stagger_ns = (n_tiles >= 4 * (int64_t)sp.n_d) ? env_int("FSNERF_BWD_STAGGER_NS", 30000) : 0;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   RG.prod = reinterpret_cast<uint32_t*>(ws);
+  RG.tile_ctr = RG.prod + 255;
   RG.cons = RG.prod + 256;
-  RG.base = ws + kFlagBytes;
+  RG.row_cap = tile_row_cap(n_tiles, sp.n_d);
+  RG.tile_of = reinterpret_cast<int32_t*>(ws + kFlagBytes);
+  RG.base = ws + kFlagBytes + tile_table_bytes(n_tiles, sp.n_d);
   static_assert((256 + kNumSMs * kMaxRingDepth) * 4 <= kFlagBytes, "flag block too small");
   {
     cudaError_t e = cudaMemsetAsync(ws, 0, kFlagBytes, st);

@@ -161,14 +161,14 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
   if (warp >= kWarpProd0) {
     // ------------------------------------------------ weight producers
     IssueBars IB{bar_w_full, bar_w_empty, bar_token, sbase + S::ring};
-    producer_loop<kStages>(tab, IB, args.packed, n_tiles, warp - kWarpProd0, lane, blockIdx.x, gridDim.x);
+    producer_loop<kStages>(tab, IB, args.packed, TileSeq{nullptr, (int64_t)blockIdx.x, (int64_t)gridDim.x, n_tiles}, warp - kWarpProd0, lane);
   } else if (warp >= kWarpMma) {
     // ------------------------------------------------ MMA issuers (mlp_issue.cuh)
     // Within a layer the encoding chunk (smem operand, independent of the previous epilogue)
     // goes FIRST in the table: it fills the bubble while the epilogue converts chunk 0.
     if (tmem_base != 0) __trap();  // 512 columns = the whole tensor memory
     IssueBars IB{bar_w_full, bar_w_empty, bar_token, sbase + S::ring};
-    issuer_loop<kStages>(tab, IB, sbase, n_tiles, (uint32_t)(warp - kWarpMma), lane, args.trace, blockIdx.x, gridDim.x);
+    issuer_loop<kStages>(tab, IB, sbase, TileSeq{nullptr, (int64_t)blockIdx.x, (int64_t)gridDim.x, n_tiles}, (uint32_t)(warp - kWarpMma), lane, args.trace);
   } else if (warp >= kWarpEnc0) {
     // ------------------------------------------------ encoders (thread = sample row)
     const int row = (warp - kWarpEnc0) * 32 + lane;

@@ -86,13 +86,48 @@ __host__ __device__ __forceinline__ uint32_t relu_bits_word_off(int chunk, int h
   return (uint32_t)(((chunk * 2 + half) * kTileM + row) * 4);
 }
 
+// ------------------------------------------------------------------ tile sequence of a CTA
+// Static: tiles first, first + stride, ... < n_tiles.  Dynamic (feed != nullptr): one thread of the
+// CTA claims tiles from a global counter a little ahead of their use and publishes them in shared
+// memory: feed[0] = tiles claimed so far (monotonic), feed[1 + (i & 3)] = tile of iteration i or -1
+// when the work has run out.  Every role warp asks for iteration i and gets the same answer.
+struct TileSeq {
+  volatile int* feed;
+  int64_t first, stride, n_tiles;
+  __device__ __forceinline__ int64_t get(uint32_t titer) const {
+    if (feed == nullptr) {
+      const int64_t t = first + (int64_t)titer * stride;
+      return t < n_tiles ? t : -1;
+    }
+    uint32_t spins = 0;
+    while (feed[0] <= (int)titer) {
+      __nanosleep(32);
+      if (++spins > (1u << 24)) { printf("fsnerf: tile feed timeout blk %d thr %d\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+    return feed[1 + (titer & 3u)];
+  }
+  // "is there a tile for iteration titer", for a warp that must stay provably converged (the MMA
+  // issuers): exits and result are warp votes
+  __device__ __forceinline__ bool has_converged(uint32_t titer) const {
+    if (feed == nullptr) return first + (int64_t)titer * stride < n_tiles;
+    uint32_t spins = 0;
+    while (!__all_sync(0xffffffffu, feed[0] > (int)titer)) {
+      if (++spins > (1u << 26)) {
+        if ((threadIdx.x & 31) == 0) printf("fsnerf: tile feed timeout blk %d thr %d\n", blockIdx.x, threadIdx.x);
+        __trap();
+      }
+    }
+    return __all_sync(0xffffffffu, feed[1 + (titer & 3u)] >= 0);
+  }
+};
+
 // ------------------------------------------------------------------ weight producers
 // Producer `me` of kProdWarps streams every kProdWarps-th stage: L2 -> smem, one bulk copy.
 template <int kStages>
 __device__ __forceinline__ void producer_loop(const IssueTable& tab, const IssueBars& B, const uint8_t* packed,
-                                              int64_t n_tiles, int me, int lane, int64_t tile0, int64_t tile_stride) {
+                                              const TileSeq& seq, int me, int lane) {
   uint32_t cnt = 0;
-  for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
+  for (uint32_t titer = 0; seq.get(titer) >= 0; ++titer) {
     for (int j = 0; j < tab.n; ++j, ++cnt) {
       if ((int)(cnt % kProdWarps) != me) continue;
       const uint32_t stage = cnt % kStages, phase = (cnt / kStages) & 1;
@@ -112,9 +147,9 @@ __device__ __forceinline__ void producer_loop(const IssueTable& tab, const Issue
 // own divergent path) streams every kProdWarps-th stage.
 template <int kStages>
 __device__ __forceinline__ void producer_loop_thread(const IssueTable& tab, const IssueBars& B, const uint8_t* packed,
-                                                     int64_t n_tiles, int me, int64_t tile0, int64_t tile_stride) {
+                                                     const TileSeq& seq, int me) {
   uint32_t cnt = 0;
-  for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
+  for (uint32_t titer = 0; seq.get(titer) >= 0; ++titer) {
     for (int j = 0; j < tab.n; ++j, ++cnt) {
       if ((int)(cnt % kProdWarps) != me) continue;
       const uint32_t stage = cnt % kStages, phase = (cnt / kStages) & 1;
@@ -133,17 +168,16 @@ __device__ __forceinline__ void producer_loop_thread(const IssueTable& tab, cons
 // clock64 timeline [tile iteration < 4][layer][k]: k = 0 layer reached, 1 first MMA, 2 committed.
 template <int kStages>
 __device__ __forceinline__ void issuer_loop(const IssueTable& tab, const IssueBars& B, uint32_t sbase,
-                                            int64_t n_tiles, uint32_t me, int lane, long long* trace,
-                                            int64_t tile0, int64_t tile_stride) {
+                                            const TileSeq& seq, uint32_t me, int lane, long long* trace) {
   const uint32_t issue = (lane == 0) ? 1u : 0u;
   const int n_rec = tab.n;
-  int64_t tile = tile0;
   uint32_t titer = 0;
   int j = (int)me;
-  if (j >= n_rec) { j -= n_rec; tile += tile_stride; ++titer; }
+  if (j >= n_rec) { j -= n_rec; ++titer; }
+  bool more = seq.has_converged(titer);
   uint32_t stage = me % kStages, wpar = 0, tok_par = me ? 0u : 1u;
   const bool tr = trace != nullptr && blockIdx.x == 0 && lane == 0;
-  while (tile < n_tiles) {
+  while (more) {
     const IssueRec& R = tab.rec[j];
     const uint32_t flags = R.flags, idesc = R.idesc;
     const bool is_tmem = flags & kRecTmem, first = flags & kRecFirst;
@@ -185,11 +219,12 @@ __device__ __forceinline__ void issuer_loop(const IssueTable& tab, const IssueBa
     stage += kMmaWarps;
     if (stage >= (uint32_t)kStages) { stage -= kStages; wpar ^= 1u; }
     if (j >= n_rec) {
-      j -= n_rec; tile += tile_stride;
+      j -= n_rec;
+      more = seq.has_converged(titer + 1);
       // the next tile's first layer overwrites TMEM region 0, which the last layer still reads
       // as its A operand: let the tensor pipe drain first (that barrier completes last_acc_n
       // times per tile)
-      if (tile < n_tiles) mbar_wait_converged(sbase + tab.last_acc_off, ((titer + 1) * tab.last_acc_n - 1) & 1u);
+      if (more) mbar_wait_converged(sbase + tab.last_acc_off, ((titer + 1) * tab.last_acc_n - 1) & 1u);
       ++titer;
     }
   }

@@ -6,11 +6,11 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from fsnerf_b200 import _lib  # noqa: E402
+from fsnerf_b200 import _lib, ops  # noqa: E402
 from fsnerf_b200.engine import HotPath  # noqa: E402
 
 dev = torch.device("cuda:0")
-hp = HotPath(device=dev)
+hp = HotPath(device=dev, n_coarse=int(os.environ.get("N_COARSE", "64")), n_fine=int(os.environ.get("N_FINE", "128")))
 R = 4096
 g = torch.Generator().manual_seed(0)
 o = (torch.tensor([0.0, 0, 4.0]) + 0.05 * torch.randn(R, 3, generator=g)).to(dev)
@@ -21,11 +21,19 @@ for _ in range(2):
 torch.cuda.synchronize()
 trace = torch.zeros(8192, dtype=torch.int64, device=dev)
 _lib.load().fsnerf_debug_set_trace(_lib.ptr(trace))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ops.profile_enable(True)
 hp.train_step(o, d, gt)   # the fine pass (last) overwrites the coarse pass's counters
 torch.cuda.synchronize()
+print("event times of this step:", {k: round(v[0], 3) for k, v in ops.profile_read().items() if k.startswith("mlp")})
+ops.profile_enable(False)
 _lib.load().fsnerf_debug_set_trace(None)
 s = trace.cpu()[1024:1024 + 148 * 8].view(148, 8).double() / 1e3
-n_w = int(os.environ.get("FSNERF_BWD_WGRAD_CTAS", "50"))
+g_ = trace.cpu()[6144:6144 + 2 * 148].view(148, 2).double()
+g_ = g_[g_[:, 0] > 0]
+print(f"last launch on the global timer: first CTA start -> last CTA end {(g_[:, 1].max() - g_[:, 0].min()) / 1e6:.3f} ms; "
+      f"start spread {(g_[:, 0].max() - g_[:, 0].min()) / 1e3:.1f} us; end spread {(g_[:, 1].max() - g_[:, 1].min()) / 1e3:.1f} us")
+n_w = int(os.environ.get("FSNERF_BWD_WGRAD_CTAS", "58"))  # must match the library default when unset
 n_d = 148 - n_w
 dg, wg = s[:n_d], s[n_d:]
 print(f"dgrad CTAs ({n_d}), kcycles mean [min..max]:")
