@@ -74,6 +74,7 @@ class _NeRFFunction(torch.autograd.Function):
                          device=out.device)
         ops.mlp_backward(module.cfg, module._flat, ctx.packed, ctx.P, ctx.stash, out,
                          d_out.contiguous(), grads, ws)
+        module._last_flat_grad = grads
         views = [grads[o:o + n].view(p.shape) for (o, n), p in zip(module._layout, module._param_list())]
         return (None, None, None, None, *views)
 
@@ -117,11 +118,17 @@ class NeRF(nn.Module):
 
     # ---- flat parameter buffer ------------------------------------------------
     def _param_list(self):
-        return [p for _, p in self.named_parameters()]
+        """parameters in state-dict order (cached: the kernels' layout is fixed at construction)"""
+        pl = self.__dict__.get("_plist")
+        if pl is None:
+            pl = [p for _, p in self.named_parameters()]
+            self.__dict__["_plist"] = pl
+        return pl
 
     def _rehome(self, device, dtype=torch.float32):
         """(Re)create the flat fp32 buffer on `device` and make every parameter a
         view into it (state_dict keys/shapes unchanged)."""
+        self.__dict__.pop("_plist", None)
         plist = self._param_list()
         if [tuple(p.shape) for p in plist] and len(plist) != len(self._layout):
             raise FsnerfError("NeRF: parameter list does not match the kernel layout")

@@ -5,6 +5,7 @@ structures.  Sampling (stratified + hierarchical sample_pdf, per
 BASELINE.json north_star, standing in for nerfacc's occupancy-grid sampler),
 the MLP and the compositor run in the CUDA kernels of libfsnerf_b200.so.
 """
+import weakref
 from typing import Optional, Tuple
 
 import numpy as np
@@ -18,6 +19,28 @@ from ..utils import utilities as U
 to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)  # noqa: E731  (reference :22)
 
 
+class _Token:
+    """lifetime marker of one forward's claim on a model's cached scratch buffers"""
+    __slots__ = ("__weakref__",)
+
+
+def _claim(model, key, nbytes, device):
+    """A device scratch buffer cached on the model (the multi-GB activation stash and the backward
+    ring are the same size every step of the reference's loop: no allocator round trip per step).
+    A buffer still claimed by a live autograd graph (two forwards before a backward) is left alone
+    and a fresh one is handed out.  -> (buffer, token); drop the token to release the claim."""
+    cache = model.__dict__.setdefault("_scratch", {})
+    buf, owner = cache.get(key, (None, None))
+    busy = owner is not None and owner() is not None
+    if buf is None or busy or buf.numel() < nbytes or buf.device != device:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        if busy:
+            return buf, _Token()  # one-off: the cached buffer stays with its owner
+    tok = _Token()
+    cache[key] = (buf, weakref.ref(tok))
+    return buf, tok
+
+
 class _RenderFunction(torch.autograd.Function):
     """rays + intervals -> MLP (fused encode + tcgen05 MLP) -> compositing.
     One autograd node so that loss.backward() (src/run-nerf.py:282) reaches the
@@ -27,23 +50,21 @@ class _RenderFunction(torch.autograd.Function):
     def forward(ctx, model, rays_o, rays_d, ts, te, bkgd, flags, need_grad, *params):
         R, S = ts.shape
         packed = model._refresh_packed()
-        stash = None
+        stash = tok = None
         if need_grad:
-            stash = torch.empty(ops.mlp_stash_bytes(model.cfg, R * S), dtype=torch.uint8, device=ts.device)
+            stash, tok = _claim(model, "stash", ops.mlp_stash_bytes(model.cfg, R * S), ts.device)
         raw = ops.mlp_forward(model.cfg, model._flat, packed, rays_o=rays_o, rays_d=rays_d,
                               t_starts=ts, t_ends=te, mask_pos=model.mask_pos,
                               mask_dir=model.mask_dir, stash=stash)
         bk = None if bkgd is None else bkgd.detach()
-        rgb, op, dp, w, al, tr = ops.composite_forward(raw.view(R, S, 4), ts, te, bkgd=bk, flags=flags,
-                                                       extras=True)
-        ctx.model, ctx.packed, ctx.stash, ctx.flags, ctx.shape = model, packed, stash, flags, (R, S)
+        rgb, op, dp, w, _, _ = ops.composite_forward(raw.view(R, S, 4), ts, te, bkgd=bk, flags=flags)
+        ctx.model, ctx.packed, ctx.stash, ctx.tok, ctx.flags, ctx.shape = model, packed, stash, tok, flags, (R, S)
         ctx.has_bkgd = bkgd is not None
         ctx.save_for_backward(raw, ts, te, bk if bk is not None else raw.new_empty(0))
-        ctx.mark_non_differentiable(raw, al, tr)
-        return rgb, op, dp, w, raw, al, tr
+        return rgb, op, dp, w, raw
 
     @staticmethod
-    def backward(ctx, d_rgb, d_op, d_dp, d_w, _d_raw, _d_al, _d_tr):
+    def backward(ctx, d_rgb, d_op, d_dp, d_w, d_raw_in):
         model = ctx.model
         raw, ts, te, bk = ctx.saved_tensors
         R, S = ctx.shape
@@ -53,17 +74,77 @@ class _RenderFunction(torch.autograd.Function):
                                              zero(d_op, (R, 1)), zero(d_dp, (R, 1)),
                                              None if d_w is None else d_w.contiguous(), bkgd=bk,
                                              flags=ctx.flags, want_d_bkgd=ctx.has_bkgd)
+        if d_raw_in is not None:
+            # gradients that reach the raw samples directly, e.g. the occlusion regulariser on
+            # extras["sigmas"] (src/run-nerf.py:260-264): added to the compositor's
+            d_raw = d_raw.view(-1, 4).add_(d_raw_in.reshape(-1, 4))
         grads = torch.zeros_like(model._flat)
-        ws = torch.empty(ops.mlp_bwd_workspace_bytes(model.cfg, R * S), dtype=torch.uint8, device=raw.device)
+        ws, wtok = _claim(model, "bwd_ws", ops.mlp_bwd_workspace_bytes(model.cfg, R * S), raw.device)
         ops.mlp_backward(model.cfg, model._flat, ctx.packed, R * S, ctx.stash, raw, d_raw.view(-1, 4), grads, ws)
+        del wtok
+        ctx.tok = ctx.stash = None  # the stash can be reused by the next forward
+        model._last_flat_grad = grads  # parallel.allreduce_module_gradients reduces this buffer in one collective
         views = [grads[o:o + n].view(p.shape) for (o, n), p in zip(model._layout, model._param_list())]
         return (None, None, None, None, None, d_bk, None, None, *views)
+
+
+class _LazyExtras(dict):
+    """nerfacc's extras dict (weights / alphas / trans / sigmas / rgbs).  The reference's loop reads
+    only ``sigmas`` (src/run-nerf.py:262): ``alphas`` and ``trans`` are computed on first access
+    instead of being written by every compositing launch."""
+
+    def __init__(self, lazy, *a, **kw):
+        super().__init__(*a, **kw)
+        self._lazy = lazy
+
+    def _materialise(self):
+        if self._lazy is not None:
+            raw, ts, te, bk, flags = self._lazy
+            self._lazy = None
+            with torch.no_grad():
+                *_, al, tr = ops.composite_forward(raw.detach().view(ts.shape[0], ts.shape[1], 4), ts, te, bkgd=bk,
+                                                   flags=flags, extras=True)
+            dict.__setitem__(self, "alphas", al.reshape(-1))
+            dict.__setitem__(self, "trans", tr.reshape(-1))
+
+    def __missing__(self, key):
+        if key in ("alphas", "trans") and self._lazy is not None:
+            self._materialise()
+            return dict.__getitem__(self, key)
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or (key in ("alphas", "trans") and self._lazy is not None)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    # enumerating the dict shows every key nerfacc's has
+    def __iter__(self):
+        self._materialise()
+        return dict.__iter__(self)
+
+    def __len__(self):
+        self._materialise()
+        return dict.__len__(self)
+
+    def keys(self):
+        self._materialise()
+        return dict.keys(self)
+
+    def items(self):
+        self._materialise()
+        return dict.items(self)
+
+    def values(self):
+        self._materialise()
+        return dict.values(self)
 
 
 def volume_render(model, rays_o, rays_d, t_starts, t_ends, render_bkgd=None, flags=0):
     """Stands in for ``nerfacc.volrend.rendering`` + the ``rgb_sigma_fn`` closure
     (reference :76-96) on a dense [R,S] sample layout.
-    -> (rgb[R,3], opacity[R,1], depth[R,1], weights[R,S], raw[R*S,4], alphas[R,S], trans[R,S])"""
+    -> (rgb[R,3], opacity[R,1], depth[R,1], weights[R,S], raw[R*S,4])"""
     params = model._param_list()
     # (grad mode is always off inside Function.forward, so decide here)
     need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or (
@@ -120,7 +201,7 @@ class HierarchicalEstimator(nn.Module):
         if self.n_fine > 0:
             bk = (torch.ones(3, device=dev) if white_bkgd else None)
             if torch.is_grad_enabled() or stratified:
-                rgb_c, op_c, dp_c, w_c, *_ = volume_render(self.proposal_model, rays_o, rays_d, ts, te, bk)
+                rgb_c, op_c, dp_c, w_c, _ = volume_render(self.proposal_model, rays_o, rays_d, ts, te, bk)
                 self.last = dict(rgb_coarse=rgb_c, opacity_coarse=op_c, depth_coarse=dp_c,
                                  weights_coarse=w_c, t_starts_coarse=ts, t_ends_coarse=te)
             else:
@@ -316,10 +397,9 @@ def render_rays(rays_o: Tensor, rays_d: Tensor, estimator, model: nn.Module, tra
     S = t_starts.numel() // max(R, 1)
     ts, te = t_starts.view(R, S), t_ends.view(R, S)
     render_bkgd = white_bkgd * torch.ones((3,), device=device, requires_grad=train)
-    rgb, opacity, depth, weights, raw, alphas, trans = volume_render(model, rays_o, rays_d, ts, te,
-                                                                     render_bkgd)
-    extras = dict(weights=weights.reshape(-1), alphas=alphas.reshape(-1), trans=trans.reshape(-1),
-                  sigmas=raw[:, 3], rgbs=raw[:, :3])
+    rgb, opacity, depth, weights, raw = volume_render(model, rays_o, rays_d, ts, te, render_bkgd)
+    extras = _LazyExtras((raw, ts, te, render_bkgd.detach(), 0), weights=weights.reshape(-1),
+                         sigmas=raw[:, 3], rgbs=raw[:, :3])
     extras.update(getattr(estimator, "last", {}))
     t_vals = (t_starts + t_ends) / 2.0
     return (rgb, opacity, depth, extras), ray_indices, t_vals

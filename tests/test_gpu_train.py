@@ -415,3 +415,77 @@ def test_reference_run_loop_on_dropin_modules(dev, sampler, tmp_path):
     assert np.isfinite(res["val_psnr"]) and 0.0 < res["val_ssim"] <= 1.0
     assert res["frames"] == (3, 32, 32, 3) and res["d_frames"] == (3, 32, 32)
     assert os.path.exists(res["checkpoint"]) and abs(res["lr_final"] - 5e-5) < 1e-6
+
+
+def test_sigmas_extra_carries_gradient(dev):
+    """extras['sigmas'] is the reference's hook for the occlusion regulariser
+    (src/run-nerf.py:260-264): a loss on it must reach the model parameters on the dense
+    (hierarchical) path exactly as it does when the samples are evaluated by model(x, dirs)."""
+    from fsnerf_b200.core.models import NeRF
+    from fsnerf_b200.core.loss import OcclusionRegularizer
+    from fsnerf_b200.render.rendering import render_rays, HierarchicalEstimator
+    R, Sc = 256, 64
+    _, _, _, _, o, d, gt = _scene_rays(R, seed=7)
+    us = np.random.default_rng(3).random((R, Sc), dtype=f32)
+    kw = {"pos_fn": {"n_freqs": 10, "log_space": True}, "dir_fn": {"n_freqs": 4, "log_space": True}}
+    model = NeRF(3, 3, 8, 256, [4], **kw).to(dev)
+    model.load_state_dict(omlp.init_state_dict(seed=42))
+    est = HierarchicalEstimator(near=2.0, far=6.0, n_coarse=Sc, n_fine=0)
+    est.set_uniforms(torch.from_numpy(us).to(dev), None)
+    ro, rd = torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev)
+    (rgb, _, _, extras), ri, tv = render_rays(ro, rd, est, model, train=True, white_bkgd=True, device=dev)
+    occ = OcclusionRegularizer(0.5, 2.0, "linear")
+    loss = torch.nn.functional.mse_loss(rgb, torch.from_numpy(gt).to(dev)) + occ(extras["sigmas"], tv, ri)
+    loss.backward()
+    g_dense = {n: p.grad.clone() for n, p in model.named_parameters()}
+    assert all(g.abs().max().item() > 0 for g in g_dense.values())
+    # the same loss with the samples evaluated by model(x, dirs) (the packed path's closure)
+    model.zero_grad()
+    ts, te = est._dense
+    tm = ((ts + te) / 2).reshape(-1)
+    x = ro[ri] + rd[ri] * tm[:, None]
+    raw = model(x, rd[ri])
+    from fsnerf_b200 import ops as fops
+    w = fops.composite_forward(raw.detach().view(R, Sc, 4), ts, te, bkgd=torch.ones(3, device=dev))[3]
+    sig_only = occ(raw[:, 3], tv, ri)
+    sig_only.backward()
+    g_sig = {n: p.grad.clone() for n, p in model.named_parameters()}
+    # dense-path gradient = gradient of the rgb term + gradient of the sigma term
+    model.zero_grad()
+    est.set_uniforms(torch.from_numpy(us).to(dev), None)
+    (rgb2, *_), _, _ = render_rays(ro, rd, est, model, train=True, white_bkgd=True, device=dev)
+    torch.nn.functional.mse_loss(rgb2, torch.from_numpy(gt).to(dev)).backward()
+    for n, p in model.named_parameters():
+        want = p.grad + g_sig[n]
+        rel = ((g_dense[n] - want).norm() / want.norm().clamp_min(1e-12)).item()
+        assert rel < 1e-2, (n, rel)  # two bf16 evaluations of the same samples (x computed in-kernel vs by torch)
+    assert sum(g.abs().sum().item() for g in g_sig.values()) > 0 and w.shape == (R, Sc)
+
+
+def test_two_forwards_before_backward(dev):
+    """the scratch buffers cached on the model are not shared by two live autograd graphs"""
+    from fsnerf_b200.core.models import NeRF
+    from fsnerf_b200.render.rendering import render_rays, HierarchicalEstimator
+    R, Sc = 256, 32
+    _, _, _, _, o, d, gt = _scene_rays(2 * R, seed=9)
+    us = np.random.default_rng(5).random((2 * R, Sc), dtype=f32)
+    kw = {"pos_fn": {"n_freqs": 10, "log_space": True}, "dir_fn": {"n_freqs": 4, "log_space": True}}
+    model = NeRF(3, 3, 8, 256, [4], **kw).to(dev)
+    model.load_state_dict(omlp.init_state_dict(seed=42))
+    est = HierarchicalEstimator(near=2.0, far=6.0, n_coarse=Sc, n_fine=0)
+    cu = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+
+    def loss_of(sl):
+        est.set_uniforms(cu(us[sl]), None)
+        (rgb, *_), _, _ = render_rays(cu(o[sl]), cu(d[sl]), est, model, train=True, white_bkgd=True, device=dev)
+        return torch.nn.functional.mse_loss(rgb, cu(gt[sl]))
+    a, b = slice(0, R), slice(R, 2 * R)
+    la, lb = loss_of(a), loss_of(b)  # two graphs alive at once
+    (la + lb).backward()
+    g_joint = [p.grad.clone() for p in model.parameters()]
+    model.zero_grad()
+    loss_of(a).backward()
+    loss_of(b).backward()  # accumulates
+    for gj, p in zip(g_joint, model.parameters()):
+        rel = ((gj - p.grad).norm() / p.grad.norm().clamp_min(1e-12)).item()
+        assert rel < 1e-4, rel
