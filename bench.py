@@ -562,7 +562,7 @@ def main():
     for k in flops:
         if k not in kms:
             continue
-        t = kms[k] + (kms.get(0.0) if k == "mlp_bwd_fused" else 0.0)
+        t = kms[k] + (kms.get("mlp_heads_wgrad", 0.0) if k == "mlp_bwd_fused" else 0.0)
         tf = flops[k] / (t / 1e3) / 1e12
         tb, tsrc = ncu_traffic("mlp_bwd_fused_kernel" if k == "mlp_bwd_fused" else k)
         n_launch = prof[k][1] / K

