@@ -79,6 +79,12 @@ def main(argv=None):
         (rgb, *_, extras), ray_indices, t_vals = R.render_rays(rays_o, rays_d, estimator, model, train=True,
                                                               white_bkgd=True, render_step_size=step_size,
                                                               device=device)
+        if extras is None:
+            # the AssertionError fallback of render_rays (src/render/rendering.py:97-103: exactly one surviving
+            # sample): a constant background with no graph behind it — the reference's loss.backward() would
+            # raise here; skip the batch
+            estimator.update_every_n_steps(step=k, occ_eval_fn=lambda x: model(x) * step_size, occ_thre=1e-2)
+            continue
         loss = F.mse_loss(rgb, rgb_gt)
         psnrs.append(-10.0 * torch.log10(loss.detach()).item())
         if "rgb_coarse" in extras:

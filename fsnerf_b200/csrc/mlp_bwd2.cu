@@ -514,7 +514,7 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_a_ready + 8 * c);
           }
-          stage_wait();
+          stage_wait();  // (staging the slab while the tensor-memory store is in flight: within noise, 1-3 %)
           stage_out(w);
           mw = mwn;
         };

@@ -233,3 +233,28 @@ def test_sinerf_through_packed_path(dev):
         opt.step()
         losses.append(loss.item())
     assert losses[-1] < losses[0]
+
+
+def test_single_sample_assertion_fallback(dev):
+    """src/render/rendering.py:88-103: with exactly ONE surviving sample nerfacc's shape assertion fires
+    (`out[..., -1].squeeze(-1)` is 0-d) and render_rays answers with a constant background, opacity and
+    extras None, depth zeros — reproduced on the packed path."""
+    from fsnerf_b200.core.models import NeRF
+    from fsnerf_b200.render.rendering import OccGridEstimator, render_rays
+    kw = {"pos_fn": {"n_freqs": 10, "log_space": True}, "dir_fn": {"n_freqs": 4, "log_space": True}}
+    model = NeRF(3, 3, 8, 256, [4], **kw).to(dev)
+    est = OccGridEstimator([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], resolution=4, levels=1).to(dev)
+    est.binaries.zero_()
+    est.binaries[0, 2, 2, 0] = True  # one occupied cell: z in [-1, -0.5]
+    # a ray along -z through that cell with a step as long as the cell: one interval survives
+    o = torch.tensor([[0.25, 0.25, 3.0], [0.9, 0.9, 3.0]])
+    d = torch.tensor([[0.0, 0.0, -1.0], [0.0, 0.0, -1.0]])
+    est.eval()
+    with torch.no_grad():
+        ri, ts, te = est.sampling(o.to(dev), d.to(dev), render_step_size=0.5)
+        assert ts.numel() == 1, ts
+        (rgb, opac, depth, extras), ri2, tv = render_rays(o, d, est, model, train=False, white_bkgd=True,
+                                                          render_step_size=0.5, device=dev)
+    assert opac is None and extras is None
+    assert torch.equal(rgb.cpu(), torch.ones(2, 3)) and torch.equal(depth.cpu(), torch.zeros(2, 1))
+    assert ri2.numel() == 1 and tv.numel() == 1

@@ -45,10 +45,14 @@ def _check_adam_step(ours, ref, lr, name):
 
 def _check_grad_bar(rels, flat=None, hp=None, ref_g=None):
     """north_star bar: weight gradients within 1e-2 relative of the fp32 reference.
-    Per tensor ||g-g_ref||/||g_ref|| <= 1e-2, except layers.0.weight where the bf16
-    rounding of the 63 encoding channels alone contributes ~0.7e-2 (its high-frequency
-    columns are incoherent sums; DESIGN.md "Numerics") -> 1.5e-2; and the WHOLE
-    gradient vector must be within 1e-2."""
+    Per tensor ||g-g_ref||/||g_ref|| <= 1e-2 and the WHOLE gradient vector within 1e-2.  One
+    documented exception AT THESE SMALL BATCHES (512-768 rays): layers.0.weight, 1.1-1.3e-2.  Its
+    high-frequency columns are incoherent sums over the samples (their norm shrinks by cancellation
+    while the bf16 noise of d(pre-activation 0), 0.55 % like layers.0.bias, does not), so the same
+    absolute error is a 2.3x larger relative one.  Measured in round 2: feeding the weight-gradient
+    GEMM the encoding to 2^-17 (bf16 hi + lo images) changes nothing (0.0127 -> 0.0127), i.e. the
+    input rounding is not the cause; at the full C2 batch (4096 rays) every tensor is <= 0.7e-2
+    (tests/test_gpu_parity_hard.py::test_full_size_c2_step_against_oracle asserts 1e-2 for all)."""
     for k, r in rels.items():
         assert r < (1.5e-2 if k.endswith("layers.0.weight") else 1e-2), (k, r)
     if flat is not None:
@@ -392,7 +396,7 @@ def test_c1_coarse_only_train_step(dev):
         rels["c." + name] = ((grads[off:off + n].cpu().double() - g_ref).norm() / g_ref.norm().clamp_min(1e-12)).item()
     print("C1 grad rel err:", {k: round(v, 4) for k, v in rels.items()})
     for k, r in rels.items():
-        assert r < (1.5e-2 if k.endswith("layers.0.weight") else 1e-2), (k, r)
+        assert r < (1.5e-2 if k.endswith("layers.0.weight") else 1e-2), (k, r)  # see _check_grad_bar
     hp.train_step(o, d, gt, cu(us), None, lr=5e-4)  # apply: parameters vs the oracle's Adam step
     ours = hp.state_dict(0)
     for k in sd_ref:
@@ -409,7 +413,10 @@ def test_reference_run_loop_on_dropin_modules(dev, sampler, tmp_path):
         os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "train_dropin.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    res = mod.main(["--iters", "150", "--size", "32", "--views", "6", "--batch", "512", "--sampler", sampler,
+    # (occupancy grid: the first ~100 steps see an empty grid, and a batch with exactly one surviving sample
+    # takes the reference's background fallback and is skipped: give it more steps to bootstrap)
+    res = mod.main(["--iters", "150" if sampler == "hierarchical" else "300", "--size", "32", "--views", "6",
+                    "--batch", "512", "--sampler", sampler,
                     "--out", str(tmp_path)])
     assert res["train_psnr_last"] > res["train_psnr_first"] + 2.0, res  # it learns the scene
     assert np.isfinite(res["val_psnr"]) and 0.0 < res["val_ssim"] <= 1.0
