@@ -158,6 +158,14 @@ class NeRF(nn.Module):
         """fp32 -> packed bf16 operand image (cheap: one small launch)."""
         if self._flat.device.type != "cuda":
             raise FsnerfError("NeRF: move the model to a CUDA device first (no CPU path)")
+        # copy.deepcopy(model) / load_state_dict(assign=True) give the parameters their own storage:
+        # the kernels would then read a stale flat buffer.  Re-home (copies the parameters' current
+        # values into a fresh flat buffer and re-views them) when the aliasing is broken.
+        base = self._flat.data_ptr()
+        for (o, _), p in zip(self._layout, self._param_list()):
+            if p.data_ptr() != base + 4 * o:
+                self._rehome(p.device)
+                break
         self._packed = ops.mlp_pack(self.cfg, self._flat, self._packed)
         return self._packed
 

@@ -125,6 +125,7 @@ int build_program(const fsnerf_net_cfg* cfg, MlpProgram* P) {
   }
   P->dstash_tile_bytes = dst;
   P->n_blocks_bwd = blk - P->n_blocks_fwd;
+  FS_REQUIRE(blk <= 192, "net cfg: %d operand blocks exceed the pack table (192): fewer layers", blk);
   P->small_off = (int64_t)blk * kBlockBytes;
   P->packed_bytes = P->small_off + (int64_t)kSmallFloats * 4;
   return FSNERF_OK;
@@ -232,7 +233,10 @@ extern "C" int fsnerf_mlp_pack(const fsnerf_net_cfg* cfg, const float* params, v
   if (rc != FSNERF_OK) return rc;
   FS_REQUIRE(params && packed, "mlp_pack: null pointer");
   FS_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127) == 0, "mlp_pack: packed must be 128B aligned");
-  static PackTable T;  // host staging (one host thread per device, see header)
+  FS_REQUIRE(P.n_blocks_fwd + P.n_blocks_bwd <= kMaxPackBlk,
+             "mlp_pack: %d operand blocks exceed the pack table (%d): fewer layers", P.n_blocks_fwd + P.n_blocks_bwd,
+             kMaxPackBlk);
+  PackTable T;
   T.n = 0;
   for (int g = 0; g < P.n_gemm; ++g) {
     const GemmLayer& L = P.layer[g];

@@ -22,6 +22,10 @@ def _f32c(t, name):
         return None
     if not t.is_cuda:
         raise _lib.FsnerfError(f"{name}: expected a CUDA tensor (no CPU fallback)")
+    if t.device.index != torch.cuda.current_device():
+        # kernels launch on the CURRENT device's stream; function attributes are configured per device
+        raise _lib.FsnerfError(f"{name}: tensor on cuda:{t.device.index} but the current device is "
+                               f"cuda:{torch.cuda.current_device()} (wrap the call in torch.cuda.device(...))")
     if t.dtype != torch.float32 or not t.is_contiguous():
         t = t.contiguous().float()
     return t

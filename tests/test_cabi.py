@@ -68,3 +68,12 @@ def test_flatten_state_dict_layout():
     flat = ops.flatten_state_dict(cfg, sd, "cpu")
     for (o, n), name in zip(ops.mlp_param_layout(cfg), ops.state_dict_names(cfg)):
         assert torch.equal(flat[o:o + n], sd[name].reshape(-1))
+
+
+def test_deep_network_is_rejected_before_the_pack_table_overflows():
+    """12 hidden layers need 205 operand blocks > the 192-entry pack table: an error, not a host overflow"""
+    from fsnerf_b200 import ops
+    from fsnerf_b200._lib import FsnerfError
+    cfg = ops.make_cfg(n_layers=12)
+    with pytest.raises(FsnerfError):
+        ops.mlp_param_count(cfg)

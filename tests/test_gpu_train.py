@@ -496,3 +496,26 @@ def test_two_forwards_before_backward(dev):
     for gj, p in zip(g_joint, model.parameters()):
         rel = ((gj - p.grad).norm() / p.grad.norm().clamp_min(1e-12)).item()
         assert rel < 1e-4, rel
+
+
+def test_deepcopy_keeps_the_kernels_on_the_copys_weights(dev):
+    """copy.deepcopy(model) gives the copy's parameters their own storage; the copy must re-home its
+    flat kernel buffer instead of silently evaluating stale weights (EMA / best-model snapshots)."""
+    import copy
+    from fsnerf_b200.core.models import NeRF
+    kw = {"pos_fn": {"n_freqs": 10, "log_space": True}, "dir_fn": {"n_freqs": 4, "log_space": True}}
+    model = NeRF(3, 3, 8, 256, [4], **kw).to(dev)
+    model.load_state_dict(omlp.init_state_dict(seed=42))
+    x = torch.rand(512, 3, device=dev) * 2 - 1
+    d = torch.nn.functional.normalize(torch.randn(512, 3, device=dev), dim=-1)
+    with torch.no_grad():
+        y0 = model(x, d).clone()
+        snap = copy.deepcopy(model)
+        sd2 = omlp.init_state_dict(seed=7)
+        snap.load_state_dict(sd2)          # in-place update of the COPY's parameters
+        y_snap = snap(x, d)
+        y_again = model(x, d)
+    ref = omlp.nerf_forward(sd2, x.cpu(), d.cpu())
+    assert (y_snap.cpu() - ref).abs().max().item() < 5e-3      # the copy runs on ITS weights
+    assert torch.equal(y_again, y0)                             # the original is untouched
+    assert (y_snap - y0).abs().max().item() > 1e-2
