@@ -6,8 +6,8 @@ autograd for the reference's own train loop.
 
 Train step (src/run-nerf.py:232-285 with the sampler replaced per north_star):
   gen_rays* -> stratified -> coarse MLP -> composite -> sample_pdf -> fine MLP
-  -> composite -> MSE grads -> composite bwd x2 -> MLP bwd x2 -> [NCCL
-  all-reduce of the flat gradient] -> Adam on the flat buffer.
+  -> composite -> MSE grads -> composite bwd x2 -> MLP bwd x2 (heads + one fused
+  dgrad/wgrad launch each) -> [NCCL all-reduce of the flat gradient] -> Adam on the flat buffer.
 Coarse and fine networks live in ONE flat fp32 parameter/gradient/moment buffer
 so the data-parallel exchange is a single collective.
 """
@@ -190,19 +190,21 @@ class HotPath:
         d_rgb_c = ops.mse_loss_grad(o["rgb_c"], rgb_gt, scale, self.loss_sums[0:1])
         d_raw_c, _ = ops.composite_backward(o["raw_c"].view(R, self.n_coarse, 4), o["ts_c"], o["te_c"], d_rgb_c,
                                             bkgd=self.bkgd, occ=None if self.hier else occ)
-        ws_c = self._bytes("ws_c", ops.mlp_bwd_workspace_bytes(cfg, R * self.n_coarse))
+        # one ring for both passes (they run back to back on the stream): it stays L2 resident
+        ws_c = self._bytes("bwd_ws", max(ops.mlp_bwd_workspace_bytes(cfg, R * self.n_coarse),
+                                         ops.mlp_bwd_workspace_bytes(cfg, R * (self.n_coarse + self.n_fine))))
         ops.mlp_backward(cfg, self.net_params(0), self.packed[0], R * self.n_coarse, o["st_c"], o["raw_c"],
                          d_raw_c.view(-1, 4), self.net_grads(0), ws_c)
-        self.launches += 2 + 3
+        self.launches += 2 + 2  # mse, composite bwd, heads, fused dgrad+wgrad
         if self.hier:
             S = self.n_coarse + self.n_fine
             d_rgb_f = ops.mse_loss_grad(o["rgb"], rgb_gt, scale, self.loss_sums[1:2])
             d_raw_f, _ = ops.composite_backward(o["raw_f"].view(R, S, 4), o["ts_f"], o["te_f"], d_rgb_f,
                                                 bkgd=self.bkgd, occ=occ)
-            ws_f = self._bytes("ws_f", ops.mlp_bwd_workspace_bytes(cfg, R * S))
+            ws_f = ws_c
             ops.mlp_backward(cfg, self.net_params(1), self.packed[1], R * S, o["st_f"], o["raw_f"],
                              d_raw_f.view(-1, 4), self.net_grads(1), ws_f)
-            self.launches += 2 + 3
+            self.launches += 2 + 2  # mse, composite bwd, heads, fused dgrad+wgrad
         if self.world > 1:
             # the path's one real exchange: SUM of the flat fp32 gradient (both nets)
             allreduce_gradients(self.grads, self.pg)
