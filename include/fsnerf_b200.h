@@ -168,7 +168,10 @@ int fsnerf_mlp_param_layout(const fsnerf_net_cfg* cfg, int64_t* offsets, int64_t
 int64_t fsnerf_mlp_packed_bytes(const fsnerf_net_cfg* cfg);
 /* bytes of the activation stash the backward needs for n_samples */
 int64_t fsnerf_mlp_stash_bytes(const fsnerf_net_cfg* cfg, int64_t n_samples);
-/* bytes of scratch the backward needs for n_samples */
+/* bytes of scratch the backward needs for n_samples: flow-control flags, the tile table and the
+ * ring of d(pre-activation) images that its dgrad CTAs hand to its wgrad CTAs (<= ~100 MB, it does
+ * NOT grow with n_samples beyond one launch's worth of CTAs).  Reusing one workspace for every
+ * call keeps the ring L2 resident. */
 int64_t fsnerf_mlp_bwd_workspace_bytes(const fsnerf_net_cfg* cfg, int64_t n_samples);
 /* fp32 params -> packed bf16 SWIZZLE_128B operand blocks */
 int fsnerf_mlp_pack(const fsnerf_net_cfg* cfg, const float* params, void* packed, void* stream);
@@ -189,8 +192,13 @@ int fsnerf_mlp_forward(const fsnerf_net_cfg* cfg, const float* params, const voi
                        const float* x, const float* dirs, const float* mask_pos,
                        const float* mask_dir, int density_only, float* out, void* stash,
                        void* stream);
-/* Backward of fsnerf_mlp_forward: d_out [P,4] (or [P] if density_only) ->
- * grads (fp32, same layout as params; ACCUMULATED into, caller zeroes). */
+/* Backward of fsnerf_mlp_forward: d_out [P,4] -> grads (fp32, same layout as params;
+ * ACCUMULATED into, caller zeroes).  Two launches: the sigma / rgb head weight gradients (SIMT) and
+ * ONE persistent cooperative launch (<= 148 CTAs, one per SM) in which dgrad CTAs and wgrad CTAs
+ * run side by side and wait on each other through the workspace — the device must be able to
+ * hold every CTA of it at once (the launch fails otherwise; nothing else may occupy the GPU).
+ * The call resets the workspace flags itself (one small cudaMemsetAsync on `stream`).
+ * density_only backward is unsupported (the reference's sigma_fn pass runs under no_grad). */
 int fsnerf_mlp_backward(const fsnerf_net_cfg* cfg, const float* params, const void* packed,
                         int64_t n_samples, const void* stash, const float* out,
                         const float* d_out, int density_only, float* grads, void* workspace,
