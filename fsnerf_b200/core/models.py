@@ -49,6 +49,7 @@ class _NeRFFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, x, dirs, need_grad, *params):
+        ctx.set_materialize_grads(False)
         density_only = dirs is None
         if need_grad and density_only:
             raise FsnerfError("NeRF(x) (density only) is inference-only on the B200 path; the "
@@ -69,6 +70,8 @@ class _NeRFFunction(torch.autograd.Function):
     def backward(ctx, d_out):
         module = ctx.module
         (out,) = ctx.saved_tensors
+        if d_out is None:
+            return (None,) * (4 + len(module._layout))
         grads = torch.zeros_like(module._flat)
         ws = torch.empty(ops.mlp_bwd_workspace_bytes(module.cfg, ctx.P), dtype=torch.uint8,
                          device=out.device)

@@ -49,6 +49,7 @@ class _RenderFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, rays_o, rays_d, ts, te, bkgd, flags, need_grad, *params):
+        ctx.set_materialize_grads(False)  # unused outputs (weights, raw, ...) arrive as None, not as zero tensors
         R, S = ts.shape
         packed = model._refresh_packed()
         stash = tok = None
@@ -70,11 +71,11 @@ class _RenderFunction(torch.autograd.Function):
         raw, ts, te, bk = ctx.saved_tensors
         R, S = ctx.shape
         bk = bk if ctx.has_bkgd else None
-        zero = lambda g, shape: torch.zeros(shape, device=raw.device) if g is None else g.contiguous()  # noqa: E731
-        d_raw, d_bk = ops.composite_backward(raw.view(R, S, 4), ts, te, zero(d_rgb, (R, 3)),
-                                             zero(d_op, (R, 1)), zero(d_dp, (R, 1)),
-                                             None if d_w is None else d_w.contiguous(), bkgd=bk,
-                                             flags=ctx.flags, want_d_bkgd=ctx.has_bkgd)
+        cont = lambda g: None if g is None else g.contiguous()  # noqa: E731  (the kernel takes NULL for an absent gradient)
+        if d_rgb is None:
+            d_rgb = torch.zeros(R, 3, device=raw.device)
+        d_raw, d_bk = ops.composite_backward(raw.view(R, S, 4), ts, te, d_rgb.contiguous(), cont(d_op), cont(d_dp),
+                                             cont(d_w), bkgd=bk, flags=ctx.flags, want_d_bkgd=ctx.has_bkgd)
         if d_raw_in is not None:
             # gradients that reach the raw samples directly, e.g. the occlusion regulariser on
             # extras["sigmas"] (src/run-nerf.py:260-264): added to the compositor's
@@ -174,6 +175,7 @@ class HierarchicalEstimator(nn.Module):
         self.proposal_model = proposal_model
         self._u_strat = self._u_pdf = None
         self.last = {}
+        self._const = {}  # per (device, shape) constants: white background, packed ray indices
 
     def set_uniforms(self, u_strat: Optional[Tensor], u_pdf: Optional[Tensor]) -> None:
         """Explicit uniforms for the next sampling() call (parity tests feed the same
@@ -200,7 +202,11 @@ class HierarchicalEstimator(nn.Module):
                                        device=dev)
         self.last = {}
         if self.n_fine > 0:
-            bk = (torch.ones(3, device=dev) if white_bkgd else None)
+            bk = None
+            if white_bkgd:
+                bk = self._const.get(("white", dev))
+                if bk is None:
+                    bk = self._const[("white", dev)] = torch.ones(3, device=dev)
             if torch.is_grad_enabled() or stratified:
                 rgb_c, op_c, dp_c, w_c, _ = volume_render(self.proposal_model, rays_o, rays_d, ts, te, bk)
                 self.last = dict(rgb_coarse=rgb_c, opacity_coarse=op_c, depth_coarse=dp_c,
@@ -221,7 +227,10 @@ class HierarchicalEstimator(nn.Module):
             ts, te, *_ = ops.sample_pdf(ts, w_c.detach(), self.n_fine, self.far,
                                         up if stratified else None, want_aux=False)
         S = ts.shape[1]
-        ray_indices = torch.arange(R, device=dev).repeat_interleave(S)
+        ray_indices = self._const.get(("ri", dev, R, S))  # the same packed index vector every step
+        if ray_indices is None:
+            self._const = {k: v for k, v in self._const.items() if k[0] != "ri"}
+            ray_indices = self._const[("ri", dev, R, S)] = torch.arange(R, device=dev).repeat_interleave(S)
         self._dense = (ts, te)
         return ray_indices, ts.reshape(-1), te.reshape(-1)
 
@@ -237,6 +246,7 @@ class _PackedCompositeFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, raw, ts, te, offsets, bkgd):
+        ctx.set_materialize_grads(False)
         bk = None if bkgd is None else bkgd.detach()
         rgb, op, dp, w, tr, al = ops.composite_packed_forward(raw, ts, te, offsets, bkgd=bk)
         ctx.has_bkgd = bkgd is not None
