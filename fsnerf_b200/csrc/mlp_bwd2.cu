@@ -593,7 +593,7 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
   const uint32_t n_stages = (kWRingBytes / stage_bytes) < (uint32_t)kWMaxStages ? (kWRingBytes / stage_bytes) : (uint32_t)kWMaxStages;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWMaxStages; ++s) {
-      mbar_init(bar_full + 8 * s, 8);   // eight issuing threads (two lanes of each of the four producer warps)
+      mbar_init(bar_full + 8 * s, 8);   // the eight issuing threads of a slab (four lanes of two producer warps)
       mbar_init(bar_empty + 8 * s, side ? 2 + kSideWarps : 2);  // MMA commit + releaser (+ side warps)
     }
     mbar_init(bar_acc_full, 1);
@@ -615,71 +615,71 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
   {
     if (warp >= 2 && warp < 6) {
       // four producer warps (the epilogue warps, idle during the main loop): bulk copies issued
-      // by one thread do not overlap (tools/l2_bench.cu), so each stage's slab copies (8 KB
-      // each: 64 rows of one chunk image) are spread over eight issuing threads, each arming
-      // the stage barrier for its own bytes
-      const int pw = (warp - 2) * 2 + lane;  // issuing thread index (lanes 0 and 1 issue)
+      // by one thread do not overlap (~440 cycles each, tools/l2_bench.cu), so a tile's slab copies
+      // (8 KB each: 64 rows of one chunk image) are spread over SIXTEEN issuing threads — lanes
+      // 0..3 of warps 2, 3 take the tile's first slab, those of warps 4, 5 its second — each arming
+      // its stage's barrier for its own bytes: at most one or two copies per thread and tile.
+      const int pw = (warp - 2) * 4 + lane;  // issuing thread index (lanes 0..3 issue)
+      const int my_slab = (warp - 2) >> 1, my_c = pw & 7;
       const int n_cp = J.a_chunks + J.b_chunks + J.c_chunks;
-      uint32_t cnt = 0;
+      uint32_t fenced_upto = 0;
       StatClock pc{0, stats != nullptr && warp == 2 && lane == 0};
       long long st_ready = 0, st_empty = 0;
       for (uint32_t n = 0;; ++n) {
-        const uint8_t* a_img = nullptr;
-        const uint8_t* b_img = nullptr;
-        const uint8_t* c_img = nullptr;
-        uint32_t tile_id = 0;
         pc.start();
         if (!have_tile(n)) break;  // (every lane: the warp stays together)
-        if (lane < 2) {  // the n-th tile the scout found published
-          fence_proxy_async_global();
+        pc.stop(st_ready);
+        const uint32_t cnt = 2u * n + (uint32_t)my_slab;
+        const uint32_t stage = cnt % n_stages, phase = (cnt / n_stages) & 1;
+        pc.start();
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        pc.stop(st_empty);
+        if (lane < 4) {
+          if (n >= fenced_upto) {
+            // one generic -> async proxy fence covers every tile the scout has published so far
+            const uint32_t r = *ready_upto;
+            __threadfence_block();
+            fence_proxy_async_global();
+            fenced_upto = r;
+          }
           const int64_t tile = queue[2 * (n % kWQueue)];
           const uint32_t bi = queue[2 * (n % kWQueue) + 1];  // producer | its iteration << 8
           const int b = (int)(bi & 255u);
           const uint32_t q = (bi >> 8) * (uint32_t)ring.n_img + (uint32_t)J.a_img;
-          a_img = ring.base + ((size_t)b * ring.depth + q % (uint32_t)ring.depth) * kImgSlotBytes;
-          b_img = args.stash + (size_t)tile * prog.stash_tile_bytes + J.b_off;
-          c_img = args.stash + (size_t)tile * prog.stash_tile_bytes + J.c_off;
-          tile_id = (uint32_t)tile;
+          const uint8_t* a_img = ring.base + ((size_t)b * ring.depth + q % (uint32_t)ring.depth) * kImgSlotBytes;
+          const uint8_t* b_img = args.stash + (size_t)tile * prog.stash_tile_bytes + J.b_off;
+          const uint8_t* c_img = args.stash + (size_t)tile * prog.stash_tile_bytes + J.c_off;
           if (b == 0 && pw == 0 && J.cons_inc == 2) evt(args.trace, EVT_ISSUE, q);
-        }
-        pc.stop(st_ready);
-        for (int slab = 0; slab < kTileM / kSlabRows; ++slab, ++cnt) {
-          const uint32_t stage = cnt % n_stages, phase = (cnt / n_stages) & 1;
-          pc.start();
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          pc.stop(st_empty);
-          if (lane < 2) {
-            const uint32_t sa = sbase + stage * stage_bytes, sb = sa + (uint32_t)J.a_chunks * kSlabBytes;
-            int mine = 0;
-            for (int c = pw; c < n_cp; c += 8) ++mine;
-            if (pw == 0) {
-              stage_tile[stage] = tile_id;  // ordered before the arrive below (release)
-              if (stats) issue_clk[stage] = clock64();
-            }
-            uint32_t aux_bytes = 0;
-            const int64_t p0 = (int64_t)tile_id * kTileM + slab * kSlabRows;
-            if (J.head && pw == 7 && p0 < args.n_samples)
-              aux_bytes = (uint32_t)((args.n_samples - p0 < kSlabRows) ? (args.n_samples - p0) : kSlabRows) * 16u;
-            mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)mine * kSlabBytes + (J.head == 2 ? 2u : 1u) * aux_bytes);
-            if (aux_bytes) {
-              bulk_g2s(sa + aux_off + 1024, args.d_out + 4 * p0, aux_bytes, bar_full + 8 * stage);
-              if (J.head == 2) bulk_g2s(sa + aux_off, args.out + 4 * p0, aux_bytes, bar_full + 8 * stage);
-            }
-            for (int c = pw; c < n_cp; c += 8) {
-              if (c < J.a_chunks)
-                bulk_g2s(sa + c * kSlabBytes, a_img + c * kChunkBytes + slab * kSlabBytes, kSlabBytes,
-                         bar_full + 8 * stage);
-              else if (c < J.a_chunks + J.b_chunks)
-                bulk_g2s(sb + (c - J.a_chunks) * kSlabBytes, b_img + (c - J.a_chunks) * kChunkBytes + slab * kSlabBytes,
-                         kSlabBytes, bar_full + 8 * stage);
-              else
-                bulk_g2s(sb + (c - J.a_chunks) * kSlabBytes,
-                         c_img + (c - J.a_chunks - J.b_chunks) * kChunkBytes + slab * kSlabBytes, kSlabBytes,
-                         bar_full + 8 * stage);
-            }
+          const uint32_t sa = sbase + stage * stage_bytes, sb = sa + (uint32_t)J.a_chunks * kSlabBytes;
+          int mine = 0;
+          for (int c = my_c; c < n_cp; c += 8) ++mine;
+          if (my_c == 0) {
+            stage_tile[stage] = (uint32_t)tile;  // ordered before the arrive below (release)
+            if (stats) issue_clk[stage] = clock64();
           }
-          __syncwarp();
+          uint32_t aux_bytes = 0;
+          const int64_t p0 = tile * kTileM + my_slab * kSlabRows;
+          if (J.head && my_c == 7 && p0 < args.n_samples)
+            aux_bytes = (uint32_t)((args.n_samples - p0 < kSlabRows) ? (args.n_samples - p0) : kSlabRows) * 16u;
+          mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)mine * kSlabBytes + (J.head == 2 ? 2u : 1u) * aux_bytes);
+          if (aux_bytes) {
+            bulk_g2s(sa + aux_off + 1024, args.d_out + 4 * p0, aux_bytes, bar_full + 8 * stage);
+            if (J.head == 2) bulk_g2s(sa + aux_off, args.out + 4 * p0, aux_bytes, bar_full + 8 * stage);
+          }
+          for (int c = my_c; c < n_cp; c += 8) {
+            if (c < J.a_chunks)
+              bulk_g2s(sa + c * kSlabBytes, a_img + c * kChunkBytes + my_slab * kSlabBytes, kSlabBytes,
+                       bar_full + 8 * stage);
+            else if (c < J.a_chunks + J.b_chunks)
+              bulk_g2s(sb + (c - J.a_chunks) * kSlabBytes, b_img + (c - J.a_chunks) * kChunkBytes + my_slab * kSlabBytes,
+                       kSlabBytes, bar_full + 8 * stage);
+            else
+              bulk_g2s(sb + (c - J.a_chunks) * kSlabBytes,
+                       c_img + (c - J.a_chunks - J.b_chunks) * kChunkBytes + my_slab * kSlabBytes, kSlabBytes,
+                       bar_full + 8 * stage);
+          }
         }
+        __syncwarp();
       }
       if (pc.on) { stats[1] = st_ready; stats[2] = st_empty; }
     } else if (warp >= kSideWarp0 && warp < kSideWarp0 + kSideWarps && side) {
