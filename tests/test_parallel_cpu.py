@@ -82,3 +82,50 @@ def test_pixel_partition_covers_every_pixel_once():
                 assert 0 <= a < b <= H * W
                 seen[f * H * W + a: f * H * W + b] += 1
         assert (seen == 1).all()
+
+
+class _FlatNet(torch.nn.Module):
+    """stand-in for the drop-in NeRF: parameters are views of one flat buffer and the backward leaves the
+    flat gradient in `_last_flat_grad` (what fsnerf_b200.core.models.NeRF does on the device)"""
+
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Parameter(torch.zeros(3, 2))
+        self.b = torch.nn.Parameter(torch.zeros(5))
+        self._layout = [(0, 6), (8, 5)]  # 16-byte aligned offsets, like fsnerf_mlp_param_layout
+        self._last_flat_grad = None
+
+    def _param_list(self):
+        return [self.a, self.b]
+
+    def fake_backward(self, flat):
+        self._last_flat_grad = flat
+        for (o, n), p in zip(self._layout, self._param_list()):
+            p.grad = flat[o:o + n].view(p.shape)
+
+
+def _worker_modules(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    flat_net, plain = _FlatNet(), torch.nn.Linear(4, 3)
+    flat_net.fake_backward(torch.arange(16, dtype=torch.float32) * (rank + 1))
+    for p in plain.parameters():
+        p.grad = torch.full_like(p, float(rank + 1))
+    parallel.allreduce_module_gradients([flat_net, plain])
+    if rank == 0:
+        torch.save(dict(a=flat_net.a.grad.clone(), b=flat_net.b.grad.clone(), flat=flat_net._last_flat_grad.clone(),
+                        w=plain.weight.grad.clone(), bias=plain.bias.grad.clone()), os.path.join(tmp, "mod.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_allreduce_module_gradients(tmp_path):
+    """the reference-style loop's exchange: one collective per flat-buffer network (aliasing kept), a
+    coalesced copy for any other module"""
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_modules, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r = torch.load(tmp_path / "mod.pt")
+    want = torch.arange(16, dtype=torch.float32) * 3  # ranks contribute x1 and x2
+    assert torch.equal(r["flat"], want)
+    assert torch.equal(r["a"], want[0:6].view(3, 2)) and torch.equal(r["b"], want[8:13])
+    assert torch.equal(r["w"], torch.full((3, 4), 3.0)) and torch.equal(r["bias"], torch.full((3,), 3.0))
