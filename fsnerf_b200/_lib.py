@@ -34,6 +34,9 @@ SIGNATURES = {
     "fsnerf_to_ndc": (_i, [_p, _p, _l, _f, _f, _f, _p, _p, _p]),
     "fsnerf_sample_stratified": (_i, [_l, _i, _f, _f, _p, _p, _p, _p]),
     "fsnerf_sample_pdf": (_i, [_l, _i, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p]),
+    "fsnerf_sample_stratified_seeded": (_i, [_l, _i, _f, _f, C.c_uint64, _p, _p, _p]),
+    "fsnerf_sample_pdf_seeded": (_i, [_l, _i, _i, _p, _p, C.c_uint64, _f, _p, _p, _p, _p, _p, _p]),
+    "fsnerf_rng_uniform": (_i, [_l, C.c_uint64, _p, _p]),
     "fsnerf_composite_forward": (_i, [_l, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
     "fsnerf_composite_backward": (_i, [_l, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
     "fsnerf_composite_backward_occ": (_i, [_l, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p,

@@ -77,6 +77,24 @@ __global__ void to_ndc_kernel(const float* __restrict__ ro, const float* __restr
   nd[i * 3] = dx; nd[i * 3 + 1] = dy; nd[i * 3 + 2] = dz;
 }
 
+// ---- counter-based uniforms (oracle/sampling.py:rng_uniform) -------------
+// u(seed, i) in [0,1) with 24 random bits: two integer finalisers (murmur3 fmix32, then
+// lowbias32) over the element index, keyed by the two halves of the seed.  Stateless, so the
+// samplers draw their jitter in registers instead of reading a torch.rand buffer
+// (reference: torch.rand at src/render/rendering.py — any i.i.d. U[0,1) stream is equivalent).
+__device__ __forceinline__ float rng_uniform(uint64_t seed, uint64_t i) {
+  uint32_t h = (uint32_t)i * 0x9E3779B1u + (uint32_t)(i >> 32) * 0x85EBCA77u + (uint32_t)seed;
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  h += (uint32_t)(seed >> 32);
+  h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+  return (float)(h >> 8) * 0x1p-24f;
+}
+
+__global__ void rng_uniform_kernel(int64_t n, uint64_t seed, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = rng_uniform(seed, (uint64_t)i);
+}
+
 // ---- stratified (oracle/sampling.py:stratified) ----
 __device__ __forceinline__ float strat_z(int i, int S, float near, float far) {
   float t = (S > 1) ? __fdiv_rn((float)i, (float)(S - 1)) : 0.0f;
@@ -88,14 +106,14 @@ __device__ __forceinline__ float strat_z(int i, int S, float near, float far) {
 // part); every point is computed ONCE and written as t_starts[i] and t_ends[i-1].
 constexpr int kStratMaxS = 2048;
 __global__ void __launch_bounds__(256)
-stratified_kernel(int64_t n_rays, int S, float near, float far, const float* __restrict__ u,
-                  float* __restrict__ ts, float* __restrict__ te, int rays_per_block) {
+stratified_kernel(int64_t n_rays, int S, float near, float far, const float* __restrict__ u, bool seeded,
+                  uint64_t seed, float* __restrict__ ts, float* __restrict__ te, int rays_per_block) {
   __shared__ float lo[kStratMaxS], hi[kStratMaxS];
   for (int i = threadIdx.x; i < S; i += blockDim.x) {
     const float z = strat_z(i, S, near, far);
     lo[i] = (i == 0) ? z : __fmul_rn(0.5f, __fadd_rn(z, strat_z(i - 1, S, near, far)));
     hi[i] = (i == S - 1) ? z : __fmul_rn(0.5f, __fadd_rn(strat_z(i + 1, S, near, far), z));
-    if (!u) lo[i] = hi[i] = z;  // deterministic: the points themselves
+    if (!u && !seeded) lo[i] = hi[i] = z;  // deterministic: the points themselves
   }
   __syncthreads();
   const int64_t r0 = (int64_t)blockIdx.x * rays_per_block;
@@ -105,7 +123,11 @@ stratified_kernel(int64_t n_rays, int S, float near, float far, const float* __r
   for (int e = threadIdx.x; e < n; e += blockDim.x) {
     const int i = e % S;
     const float l = lo[i];
-    const float p = u ? __fadd_rn(l, __fmul_rn(__fsub_rn(hi[i], l), __ldg(u + base + e))) : l;
+    float p = l;
+    if (u || seeded) {
+      const float uv = seeded ? rng_uniform(seed, (uint64_t)(base + e)) : __ldg(u + base + e);
+      p = __fadd_rn(l, __fmul_rn(__fsub_rn(hi[i], l), uv));
+    }
     ts[base + e] = p;
     if (i > 0) te[base + e - 1] = p;
     if (i == S - 1) te[base + e] = far;
@@ -124,8 +146,8 @@ constexpr int kPdfWarps = 4;
 template <int E>
 __global__ void __launch_bounds__(kPdfWarps * 32)
 sample_pdf_kernel(int64_t n_rays, int Sc, int Sf, const float* __restrict__ z_coarse,
-                  const float* __restrict__ w_coarse, const float* __restrict__ u, float far,
-                  float* __restrict__ samples, int32_t* __restrict__ inds_out,
+                  const float* __restrict__ w_coarse, const float* __restrict__ u, bool seeded,
+                  uint64_t seed, float far, float* __restrict__ samples, int32_t* __restrict__ inds_out,
                   int32_t* __restrict__ perm_out, float* __restrict__ ts, float* __restrict__ te) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -183,7 +205,9 @@ sample_pdf_kernel(int64_t n_rays, int Sc, int Sf, const float* __restrict__ z_co
   __syncwarp();
 
   for (int k = lane; k < Sf; k += 32) {
-    float uk = u ? u[r * Sf + k] : (Sf > 1 ? __fdiv_rn((float)k, (float)(Sf - 1)) : 0.0f);
+    float uk = seeded ? rng_uniform(seed, (uint64_t)(r * Sf + k))
+               : u    ? u[r * Sf + k]
+                      : (Sf > 1 ? __fdiv_rn((float)k, (float)(Sf - 1)) : 0.0f);
     // searchsorted(right=True): number of cdf entries <= uk (cdf is increasing)
     int lo = 0, hi = nb;
     while (lo < hi) {
@@ -336,9 +360,8 @@ extern "C" int fsnerf_encode(int64_t n_points, int d_input, int n_freqs, const f
   return fsnerf_check_launch("encode");
 }
 
-extern "C" int fsnerf_sample_stratified(int64_t n_rays, int n_samples, float near, float far,
-                                        const float* u, float* t_starts, float* t_ends,
-                                        void* stream) {
+static int sample_stratified_impl(int64_t n_rays, int n_samples, float near, float far, const float* u,
+                                  bool seeded, uint64_t seed, float* t_starts, float* t_ends, void* stream) {
   FS_REQUIRE(n_samples >= 1 && n_rays >= 0, "sample_stratified: bad sizes");
   if (n_rays == 0) return FSNERF_OK;
   FS_REQUIRE(t_starts && t_ends, "sample_stratified: null output");
@@ -347,15 +370,36 @@ extern "C" int fsnerf_sample_stratified(int64_t n_rays, int n_samples, float nea
   int rays_per_block = 4096 / n_samples;  // ~4 K samples per block, at least one ray
   if (rays_per_block < 1) rays_per_block = 1;
   const int64_t blocks = (n_rays + rays_per_block - 1) / rays_per_block;
-  stratified_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n_rays, n_samples, near, far, u, t_starts,
-                                                                       t_ends, rays_per_block);
+  stratified_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      n_rays, n_samples, near, far, u, seeded, seed, t_starts, t_ends, rays_per_block);
   return fsnerf_check_launch("sample_stratified");
 }
 
-extern "C" int fsnerf_sample_pdf(int64_t n_rays, int n_coarse, int n_fine, const float* z_coarse,
-                                 const float* w_coarse, const float* u, float far, float* samples,
-                                 int32_t* inds, int32_t* perm, float* t_starts, float* t_ends,
-                                 void* stream) {
+extern "C" int fsnerf_sample_stratified(int64_t n_rays, int n_samples, float near, float far,
+                                        const float* u, float* t_starts, float* t_ends,
+                                        void* stream) {
+  return sample_stratified_impl(n_rays, n_samples, near, far, u, false, 0, t_starts, t_ends, stream);
+}
+
+extern "C" int fsnerf_sample_stratified_seeded(int64_t n_rays, int n_samples, float near, float far,
+                                               uint64_t seed, float* t_starts, float* t_ends,
+                                               void* stream) {
+  return sample_stratified_impl(n_rays, n_samples, near, far, nullptr, true, seed, t_starts, t_ends, stream);
+}
+
+extern "C" int fsnerf_rng_uniform(int64_t n, uint64_t seed, float* out, void* stream) {
+  FS_REQUIRE(n >= 0, "rng_uniform: bad size");
+  if (n == 0) return FSNERF_OK;
+  FS_REQUIRE(out, "rng_uniform: null output");
+  FsProfScope prof_("rng_uniform", stream);
+  rng_uniform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, seed, out);
+  return fsnerf_check_launch("rng_uniform");
+}
+
+static int sample_pdf_impl(int64_t n_rays, int n_coarse, int n_fine, const float* z_coarse,
+                           const float* w_coarse, const float* u, bool seeded, uint64_t seed, float far,
+                           float* samples, int32_t* inds, int32_t* perm, float* t_starts, float* t_ends,
+                           void* stream) {
   if (n_rays == 0) return FSNERF_OK;
   FS_REQUIRE(z_coarse && w_coarse && t_starts && t_ends, "sample_pdf: null pointer");
   FS_REQUIRE(n_coarse >= 3 && n_coarse - 2 <= 32 * kPdfMaxE, "sample_pdf: n_coarse must be in [3,258]");
@@ -369,7 +413,7 @@ extern "C" int fsnerf_sample_pdf(int64_t n_rays, int n_coarse, int n_fine, const
   FsProfScope prof_("sample_pdf", stream);
 #define LAUNCH_PDF(E_)                                                                          \
   sample_pdf_kernel<E_><<<(unsigned)blocks, kPdfWarps * 32, smem, (cudaStream_t)stream>>>(     \
-      n_rays, n_coarse, n_fine, z_coarse, w_coarse, u, far, samples, inds, perm, t_starts, t_ends)
+      n_rays, n_coarse, n_fine, z_coarse, w_coarse, u, seeded, seed, far, samples, inds, perm, t_starts, t_ends)
   switch ((n_coarse - 2 + 31) / 32) {
     case 1: LAUNCH_PDF(1); break;
     case 2: LAUNCH_PDF(2); break;
@@ -382,4 +426,20 @@ extern "C" int fsnerf_sample_pdf(int64_t n_rays, int n_coarse, int n_fine, const
   }
 #undef LAUNCH_PDF
   return fsnerf_check_launch("sample_pdf");
+}
+
+extern "C" int fsnerf_sample_pdf(int64_t n_rays, int n_coarse, int n_fine, const float* z_coarse,
+                                 const float* w_coarse, const float* u, float far, float* samples,
+                                 int32_t* inds, int32_t* perm, float* t_starts, float* t_ends,
+                                 void* stream) {
+  return sample_pdf_impl(n_rays, n_coarse, n_fine, z_coarse, w_coarse, u, false, 0, far, samples, inds, perm,
+                         t_starts, t_ends, stream);
+}
+
+extern "C" int fsnerf_sample_pdf_seeded(int64_t n_rays, int n_coarse, int n_fine, const float* z_coarse,
+                                        const float* w_coarse, uint64_t seed, float far, float* samples,
+                                        int32_t* inds, int32_t* perm, float* t_starts, float* t_ends,
+                                        void* stream) {
+  return sample_pdf_impl(n_rays, n_coarse, n_fine, z_coarse, w_coarse, nullptr, true, seed, far, samples, inds,
+                         perm, t_starts, t_ends, stream);
 }

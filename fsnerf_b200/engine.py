@@ -21,6 +21,8 @@ from ._lib import FsnerfError
 from .core.models import NeRF, freq_mask
 from .parallel import allreduce_gradients, loss_grad_scale
 
+_M64 = (1 << 64) - 1
+
 
 class HotPath:
     def __init__(self, n_coarse=64, n_fine=128, near=2.0, far=6.0, white_bkgd=True, device="cuda",
@@ -48,13 +50,16 @@ class HotPath:
             for i in range(n_nets):
                 net = NeRF(3, 3, n_layers, d_hidden, list(skip), **kw)
                 self.params[i * self.n_net:(i + 1) * self.n_net].copy_(net.flat_parameters())
-        self.grads = torch.zeros_like(self.params)
+        # gradient buffer with the two loss accumulators behind it: ONE fill zeroes both every step
+        self._grads_and_loss = torch.zeros(self.params.numel() + 2, device=self.device)
+        self.grads = self._grads_and_loss[:self.params.numel()]
         self.m = torch.zeros_like(self.params)
         self.v = torch.zeros_like(self.params)
         self.packed = [torch.empty(ops.mlp_packed_bytes(self.cfg), dtype=torch.uint8, device=self.device)
                        for _ in range(n_nets)]
         self.bkgd = torch.ones(3, device=self.device) if self.white_bkgd else None
         self.step = 0
+        self._seed, self._draws = int(seed), 0
         self.lr = lr
         self.pg = process_group
         if world_size is not None:
@@ -62,7 +67,9 @@ class HotPath:
         else:
             self.world = torch.distributed.get_world_size(process_group) if process_group is not None or (
                 torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
-        self.loss_sums = torch.zeros(2, device=self.device)
+        self.rank = torch.distributed.get_rank(process_group) if self.world > 1 and (
+            torch.distributed.is_available() and torch.distributed.is_initialized()) else 0
+        self.loss_sums = self._grads_and_loss[self.params.numel():]
         # in-step regularisers: occlusion (src/core/loss.py:26-60) fused into the
         # compositing backward, weight-norm penalty (src/run-nerf.py:266-279) fused into Adam
         self.occ_sum = torch.zeros(1, device=self.device)
@@ -121,10 +128,23 @@ class HotPath:
             self._packed_fresh = True
 
     # ------------------------------------------------------------------ forward
-    def _forward(self, rays_o, rays_d, u_strat, u_pdf, train):
+    def _jitter_seeds(self):
+        """Two fresh 64-bit keys (stratified, pdf) for the in-kernel uniform stream: splitmix64 of
+        (construction seed, rank, draw counter), so ranks and steps never share a stream."""
+        self._draws += 1
+        keys = []
+        for which in (0, 1):
+            z = (self._seed * 0x9E3779B97F4A7C15 + (self.rank << 40) + 2 * self._draws + which) & _M64
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+            keys.append(z ^ (z >> 31))
+        return keys
+
+    def _forward(self, rays_o, rays_d, u_strat, u_pdf, train, seeds=(None, None)):
         cfg, R = self.cfg, rays_o.shape[0]
         self._pack()
-        ts_c, te_c = ops.sample_stratified(R, self.n_coarse, self.near, self.far, u_strat, device=self.device)
+        ts_c, te_c = ops.sample_stratified(R, self.n_coarse, self.near, self.far, u_strat, device=self.device,
+                                           seed=seeds[0] if u_strat is None else None)
         st_c = self._bytes("stash_c", ops.mlp_stash_bytes(cfg, R * self.n_coarse)) if train else None
         # rendering a hierarchical model needs only the WEIGHTS of the coarse pass: skip its view
         # branch (17 % of its FLOPs) and write sigma straight into the compositor's (rgb, sigma) layout
@@ -141,7 +161,8 @@ class HotPath:
             out.update(rgb=rgb_c, opacity=op_c, depth=dp_c)
             return out
         S = self.n_coarse + self.n_fine
-        ts_f, te_f, *_ = ops.sample_pdf(ts_c, w_c, self.n_fine, self.far, u_pdf, want_aux=False)
+        ts_f, te_f, *_ = ops.sample_pdf(ts_c, w_c, self.n_fine, self.far, u_pdf, want_aux=False,
+                                        seed=seeds[1] if u_pdf is None else None)
         st_f = self._bytes("stash_f", ops.mlp_stash_bytes(cfg, R * S)) if train else None
         raw_f = ops.mlp_forward(cfg, self.net_params(1), self.packed[1], rays_o=rays_o, rays_d=rays_d,
                                 t_starts=ts_f, t_ends=te_f, mask_pos=self.mask_pos, mask_dir=self.mask_dir,
@@ -164,7 +185,9 @@ class HotPath:
                    occ_reg=None, weight_reg=None):
         """One optimisation step on this rank's ray shard.  Returns a device
         tensor [2] = (sum sq err coarse, sum sq err fine) over the local shard;
-        mean loss = value / (3 * global_rays).  u_* default to torch.rand.
+        mean loss = value / (3 * global_rays).  u_*: explicit uniforms (parity tests); by default
+        the samplers draw them in-kernel from the counter-based stream (ops.rng_uniform), so
+        the step launches no generator kernel and writes no uniform buffer.
 
         occ_reg = (a, b, func): adds core.loss.OcclusionRegularizer(a, b, func) of the output
         pass (the fine network's samples; the coarse ones when n_fine == 0) to the loss exactly
@@ -175,13 +198,8 @@ class HotPath:
         None.  self.reg_sums holds sum|w| (l1) / sum w^2 (l2) per regularised tensor."""
         cfg, R = self.cfg, rays_o.shape[0]
         G = int(global_rays) if global_rays is not None else R * self.world
-        if u_strat is None:
-            u_strat = torch.rand(R, self.n_coarse, device=self.device)
-        if u_pdf is None and self.hier:
-            u_pdf = torch.rand(R, self.n_fine, device=self.device)
-        o = self._forward(rays_o, rays_d, u_strat, u_pdf, train=True)
-        self.loss_sums.zero_()
-        self.grads.zero_()
+        o = self._forward(rays_o, rays_d, u_strat, u_pdf, train=True, seeds=self._jitter_seeds())
+        self._grads_and_loss.zero_()
         scale = loss_grad_scale(G)  # F.mse_loss 'mean' over the GLOBAL batch (src/run-nerf.py:256)
         occ = None
         if occ_reg is not None:

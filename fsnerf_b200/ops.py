@@ -72,17 +72,36 @@ def to_ndc(rays_o, rays_d, H, W, focal, near):
     return no.reshape(rays_o.shape), nd.reshape(rays_d.shape)
 
 
-def sample_stratified(n_rays, n_samples, near, far, u=None, device=None):
+def rng_uniform(n, seed, device=None):
+    """u(seed, i), i < n: the stream the seeded samplers draw from (oracle/sampling.py:rng_uniform)."""
+    out = torch.empty(n, device=device)
+    check(_lib.load().fsnerf_rng_uniform(n, int(seed) & _SEED_MASK, ptr(out), _stream()), "fsnerf_rng_uniform")
+    return out
+
+
+_SEED_MASK = (1 << 64) - 1
+
+
+def sample_stratified(n_rays, n_samples, near, far, u=None, device=None, seed=None):
+    """u: explicit uniforms [R,S]; seed: draw them in the kernel (u must be None); neither: the
+    deterministic points."""
     u = _f32c(u, "u")
     dev = u.device if u is not None else device
     ts = torch.empty(n_rays, n_samples, device=dev)
     te = torch.empty(n_rays, n_samples, device=dev)
+    if seed is not None:
+        if u is not None:
+            raise _lib.FsnerfError("sample_stratified: pass u or seed, not both")
+        check(_lib.load().fsnerf_sample_stratified_seeded(n_rays, n_samples, float(near), float(far),
+                                                          int(seed) & _SEED_MASK, ptr(ts), ptr(te), _stream()),
+              "fsnerf_sample_stratified_seeded")
+        return ts, te
     check(_lib.load().fsnerf_sample_stratified(n_rays, n_samples, float(near), float(far), ptr(u),
                                                ptr(ts), ptr(te), _stream()), "fsnerf_sample_stratified")
     return ts, te
 
 
-def sample_pdf(z_coarse, w_coarse, n_fine, far, u=None, want_aux=True):
+def sample_pdf(z_coarse, w_coarse, n_fine, far, u=None, want_aux=True, seed=None):
     z, w, u = _f32c(z_coarse, "z_coarse"), _f32c(w_coarse, "w_coarse"), _f32c(u, "u")
     R, Sc = z.shape
     dev = z.device
@@ -91,6 +110,13 @@ def sample_pdf(z_coarse, w_coarse, n_fine, far, u=None, want_aux=True):
     samples = torch.empty(R, n_fine, device=dev) if want_aux else None
     inds = torch.empty(R, n_fine, device=dev, dtype=torch.int32) if want_aux else None
     perm = torch.empty(R, Sc + n_fine, device=dev, dtype=torch.int32) if want_aux else None
+    if seed is not None:
+        if u is not None:
+            raise _lib.FsnerfError("sample_pdf: pass u or seed, not both")
+        check(_lib.load().fsnerf_sample_pdf_seeded(R, Sc, n_fine, ptr(z), ptr(w), int(seed) & _SEED_MASK,
+                                                   float(far), ptr(samples), ptr(inds), ptr(perm), ptr(ts),
+                                                   ptr(te), _stream()), "fsnerf_sample_pdf_seeded")
+        return ts, te, samples, inds, perm
     check(_lib.load().fsnerf_sample_pdf(R, Sc, n_fine, ptr(z), ptr(w), ptr(u), float(far),
                                         ptr(samples), ptr(inds), ptr(perm), ptr(ts), ptr(te),
                                         _stream()), "fsnerf_sample_pdf")

@@ -179,7 +179,9 @@ class HierarchicalEstimator(nn.Module):
 
     def set_uniforms(self, u_strat: Optional[Tensor], u_pdf: Optional[Tensor]) -> None:
         """Explicit uniforms for the next sampling() call (parity tests feed the same
-        ones to the oracle); otherwise torch.rand on the device."""
+        ones to the oracle); otherwise the samplers draw them in-kernel, keyed by a 64-bit seed
+        taken from torch's CPU generator (so torch.manual_seed reproduces a run, as it does for
+        the reference's torch.rand)."""
         self._u_strat, self._u_pdf = u_strat, u_pdf
 
     @property
@@ -196,10 +198,11 @@ class HierarchicalEstimator(nn.Module):
         dev = rays_o.device
         us, up = self._u_strat, self._u_pdf
         self._u_strat = self._u_pdf = None
-        if stratified and us is None:
-            us = torch.rand(R, self.n_coarse, device=dev)
+        seeds = (None, None)
+        if stratified and (us is None or (up is None and self.n_fine > 0)):
+            seeds = [int(v) for v in torch.empty(2, dtype=torch.int64).random_()]
         ts, te = ops.sample_stratified(R, self.n_coarse, self.near, self.far, us if stratified else None,
-                                       device=dev)
+                                       device=dev, seed=seeds[0] if stratified and us is None else None)
         self.last = {}
         if self.n_fine > 0:
             bk = None
@@ -222,10 +225,9 @@ class HierarchicalEstimator(nn.Module):
                 _, op_c, dp_c, w_c, _, _ = ops.composite_forward(raw_c.view(R, self.n_coarse, 4), ts, te, bkgd=bk)
                 self.last = dict(opacity_coarse=op_c, depth_coarse=dp_c, weights_coarse=w_c,
                                  t_starts_coarse=ts, t_ends_coarse=te)
-            if stratified and up is None:
-                up = torch.rand(R, self.n_fine, device=dev)
             ts, te, *_ = ops.sample_pdf(ts, w_c.detach(), self.n_fine, self.far,
-                                        up if stratified else None, want_aux=False)
+                                        up if stratified else None, want_aux=False,
+                                        seed=seeds[1] if stratified and up is None else None)
         S = ts.shape[1]
         ray_indices = self._const.get(("ri", dev, R, S))  # the same packed index vector every step
         if ray_indices is None:

@@ -70,6 +70,20 @@ int fsnerf_sample_pdf(int64_t n_rays, int n_coarse, int n_fine, const float* z_c
                       const float* w_coarse, const float* u, float far, float* samples,
                       int32_t* inds, int32_t* perm, float* t_starts, float* t_ends, void* stream);
 
+/* Seeded variants: the uniforms the reference draws with torch.rand (src/render/
+ * rendering.py stratified jitter / sample_pdf u) come from a stateless counter-based
+ * generator evaluated inside the kernel — element i of the [R,S] (resp. [R,Sf]) grid uses
+ * fsnerf_rng_uniform's value i for the same seed — so no uniform buffer is written or read.
+ * Results are bit-identical to the explicit-u entry points fed with that stream. */
+int fsnerf_sample_stratified_seeded(int64_t n_rays, int n_samples, float near, float far,
+                                    uint64_t seed, float* t_starts, float* t_ends, void* stream);
+int fsnerf_sample_pdf_seeded(int64_t n_rays, int n_coarse, int n_fine, const float* z_coarse,
+                             const float* w_coarse, uint64_t seed, float far, float* samples,
+                             int32_t* inds, int32_t* perm, float* t_starts, float* t_ends,
+                             void* stream);
+/* out[i] = u(seed, i) in [0,1), 24 random bits, i < n (oracle/sampling.py:rng_uniform). */
+int fsnerf_rng_uniform(int64_t n, uint64_t seed, float* out, void* stream);
+
 /* ---- (4) compositing -------------------------------------------------- */
 /* Replaces nerfacc.volrend.rendering as called at src/render/rendering.py:89-96
  * on a dense layout (S samples per ray).  raw [R,S,4]=(rgb,sigma).

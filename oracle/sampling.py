@@ -26,6 +26,32 @@ def linspace01(n):
     return (np.arange(n, dtype=f32) / f32(n - 1)).astype(f32)
 
 
+def rng_uniform(seed, n):
+    """The stateless uniform stream of the seeded samplers (include/fsnerf_b200.h:
+    fsnerf_rng_uniform; csrc/rays.cu:rng_uniform).  Element i: the low and high index words mixed
+    with the low seed word, murmur3's fmix32, plus the high seed word, the lowbias32 finaliser;
+    the top 24 bits scaled by 2^-24.  It stands in for the reference's torch.rand (src/render/
+    rendering.py), whose actual stream no test of the reference pins either."""
+    seed = int(seed) & ((1 << 64) - 1)
+    i = np.arange(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        lo = (i & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        hi = (i >> np.uint64(32)).astype(np.uint32)
+        h = lo * np.uint32(0x9E3779B1) + hi * np.uint32(0x85EBCA77) + np.uint32(seed & 0xFFFFFFFF)
+        h ^= h >> np.uint32(16)
+        h *= np.uint32(0x85EBCA6B)
+        h ^= h >> np.uint32(13)
+        h *= np.uint32(0xC2B2AE35)
+        h ^= h >> np.uint32(16)
+        h += np.uint32(seed >> 32)
+        h ^= h >> np.uint32(16)
+        h *= np.uint32(0x7FEB352D)
+        h ^= h >> np.uint32(15)
+        h *= np.uint32(0x846CA68B)
+        h ^= h >> np.uint32(16)
+    return ((h >> np.uint32(8)).astype(f32) * f32(2.0 ** -24)).astype(f32)
+
+
 def stratified(n_rays, n_samples, near, far, u=None):
     """Appendix B1.  -> z [R,S] f32 sorted points.
 

@@ -95,6 +95,53 @@ def test_sample_pdf_bit_exact(dev, R, Sc, Sf):
         np.testing.assert_array_equal(te.cpu().numpy(), ref["t_ends"])
 
 
+@pytest.mark.parametrize("seed", [0, 1, 42, 0x9E3779B97F4A7C15, (1 << 64) - 1])
+def test_seeded_samplers_bit_exact(dev, seed):
+    """In-kernel uniforms: the device stream equals oracle.sampling.rng_uniform bit for bit, and
+    the seeded samplers equal the explicit-u ones (and the oracle) fed with that stream."""
+    from fsnerf_b200 import ops
+    R, Sc, Sf = 515, 64, 128
+    n = 70000
+    np.testing.assert_array_equal(ops.rng_uniform(n, seed, device=dev).cpu().numpy(), osamp.rng_uniform(seed, n))
+    us = osamp.rng_uniform(seed, R * Sc).reshape(R, Sc)
+    up = osamp.rng_uniform(seed ^ 0x5555, R * Sf).reshape(R, Sf)
+    ts, te = ops.sample_stratified(R, Sc, 2.0, 6.0, device=dev, seed=seed)
+    z = osamp.stratified(R, Sc, 2.0, 6.0, us)
+    np.testing.assert_array_equal(ts.cpu().numpy(), z)
+    ts2, te2 = ops.sample_stratified(R, Sc, 2.0, 6.0, cu(us, dev))
+    assert torch.equal(ts, ts2) and torch.equal(te, te2)
+    w = np.random.default_rng(5).random((R, Sc), dtype=f32) ** 6
+    ref = osamp.sample_pdf(z, w, Sf, 6.0, up)
+    got = ops.sample_pdf(ts, cu(w, dev), Sf, 6.0, seed=seed ^ 0x5555)
+    for g, k in zip(got, ("t_starts", "t_ends", "samples", "inds", "perm")):
+        np.testing.assert_array_equal(g.cpu().numpy(), ref[k])
+    with pytest.raises(Exception):
+        ops.sample_stratified(R, Sc, 2.0, 6.0, cu(us, dev), seed=1)
+
+
+def test_engine_default_jitter_is_in_kernel_and_reproducible(dev):
+    """train_step without explicit uniforms: no generator launch, a fresh stream every step (the
+    weights are held fixed, so a different loss means different jitter), the same streams for
+    the same construction seed."""
+    from fsnerf_b200.engine import HotPath
+    g = torch.Generator().manual_seed(3)
+    R = 256
+    o = torch.rand(R, 3, generator=g).to(dev) * 0.1
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1).to(dev)
+    gt = torch.rand(R, 3, generator=g).to(dev)
+    runs = []
+    for _ in range(2):
+        hp = HotPath(n_coarse=16, n_fine=16, near=2.0, far=6.0, device=dev, seed=7)
+        state = torch.cuda.get_rng_state(dev)
+        losses = [hp.train_step(o, d, gt, apply_update=False).clone() for _ in range(3)]
+        assert torch.equal(state, torch.cuda.get_rng_state(dev))  # torch's device generator untouched
+        runs.append(torch.stack(losses).cpu())
+    # the loss sums are float atomics (order varies run to run): same stream <=> equal to ~1 ulp,
+    # while a different stream moves them in the 4th digit
+    torch.testing.assert_close(runs[0], runs[1], rtol=2e-6, atol=0)
+    assert (runs[0][0] - runs[0][1]).abs().max() > 1e-4 * runs[0][0].abs().max()
+
+
 # ----------------------------------------------------------- compositing
 def _comp_inputs(R, S, seed, neg_sigma=True):
     g = torch.Generator().manual_seed(seed)

@@ -448,3 +448,28 @@ def test_sinerf_mirror_matches_reference(golden):
     loss = (out * torch.linspace(0.1, 1.0, 4)).sum()
     grads = torch.autograd.grad(loss, list(model.parameters()))
     np.testing.assert_allclose([gr.double().norm().item() for gr in grads], g["g_norm"], rtol=1e-5, atol=1e-9)
+
+
+def test_rng_uniform_stream():
+    """The seeded samplers' uniform stream: the vectorised oracle against a scalar restatement
+    with Python integers (masking by hand), plus the basic statistics of a U[0,1) sample."""
+    from oracle.sampling import rng_uniform
+    M = 0xFFFFFFFF
+
+    def scalar(seed, i):
+        h = ((i & M) * 0x9E3779B1 + (i >> 32) * 0x85EBCA77 + (seed & M)) & M
+        h ^= h >> 16; h = h * 0x85EBCA6B & M; h ^= h >> 13; h = h * 0xC2B2AE35 & M; h ^= h >> 16
+        h = (h + (seed >> 32)) & M
+        h ^= h >> 16; h = h * 0x7FEB352D & M; h ^= h >> 15; h = h * 0x846CA68B & M; h ^= h >> 16
+        return (h >> 8) / float(1 << 24)
+
+    for seed in (0, 1, 42, 0x9E3779B97F4A7C15, (1 << 64) - 1):
+        u = rng_uniform(seed, 4096)
+        assert u.dtype == np.float32
+        assert [float(x) for x in u[:64]] == [scalar(seed, i) for i in range(64)]
+        assert float(u[4095]) == scalar(seed, 4095)
+    u = rng_uniform(7, 1 << 18)
+    assert 0.0 <= u.min() and u.max() < 1.0
+    assert abs(u.mean() - 0.5) < 3e-3 and abs(u.var() * 12 - 1) < 1e-2
+    assert abs(np.corrcoef(u[:-1], u[1:])[0, 1]) < 1e-2
+    assert abs(np.corrcoef(u, rng_uniform(8, 1 << 18))[0, 1]) < 1e-2
