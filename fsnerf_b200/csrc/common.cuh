@@ -143,6 +143,26 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
       "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
+// ---------------------------------------------------------------- thread-block clusters (CTA pairs)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// all threads of every CTA of the cluster (also a CTA-wide barrier)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one L2 read delivered to the same shared-memory offset of every CTA in cta_mask; each
+// destination CTA's barrier (same offset) receives the complete_tx for its copy
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes,
+                                                   uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::
+          "r"(dst_smem),
+      "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
                "r"(src_smem), "r"(bytes)
@@ -311,6 +331,15 @@ __device__ __forceinline__ void umma_commit_conv(uint32_t bar, uint32_t issue) {
       "setp.ne.b32 e, %1, 0;\n\t"
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar),
       "r"(issue)
+      : "memory");
+}
+// ... arriving on the barrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_multicast_conv(uint32_t bar, uint32_t issue, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "setp.ne.b32 e, %1, 0;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %2;\n\t}" ::"r"(bar),
+      "r"(issue), "h"(cta_mask)
       : "memory");
 }
 // registers -> TMEM: thread i of the warp writes lane (taddr.lane + i), 16 consecutive columns

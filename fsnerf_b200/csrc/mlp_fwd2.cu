@@ -89,6 +89,7 @@ struct Fwd2Args {
   int density_only;
   float* out;
   uint8_t* stash;
+  int pair;  // launched as clusters of two CTAs sharing multicast weight stages
 };
 
 template <bool kTrain>
@@ -119,6 +120,13 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
   for (int g = 0; g < prog.n_hidden; ++g)
     if (prog.layer[g].use_aux) last_pos_user = g;
   const int64_t n_tiles = (args.n_samples + kTileM - 1) / kTileM;
+  // CTA pairs (args.pair): the two CTAs of a cluster stream the SAME weight chunks in lock step,
+  // each fetching every other one from L2 for both (mlp_issue.cuh: producer_loop).  Both run the
+  // even CTA's iteration count; a tile index past the end is a dummy (computed, not stored).
+  const bool pair = args.pair != 0;
+  const int pair_rank = pair ? (int)cluster_ctarank() : -1;
+  const TileSeq seq = TileSeq::strided((int64_t)blockIdx.x, (int64_t)gridDim.x, n_tiles,
+                                       (int64_t)blockIdx.x - (pair ? pair_rank : 0));
 
   if ((sbase & 1023u) != 0) {
     if (threadIdx.x == 0) printf("fsnerf: dynamic smem base not 1024B aligned (%u)\n", sbase);
@@ -127,7 +135,7 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_w_full + 8 * s, 1);
-      mbar_init(bar_w_empty + 8 * s, 1);
+      mbar_init(bar_w_empty + 8 * s, pair ? 2 : 1);  // pair: released by both CTAs' MMAs
     }
     for (int c = 0; c < 4; ++c) mbar_init(bar_a_ready + 8 * c, kEpiWarps);
     mbar_init(bar_acc_full, kMmaWarps);
@@ -154,28 +162,30 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
     reinterpret_cast<float*>(smem + S::heads)[i] = __ldg(small + kSmallSigmaW + i);
   const float* head_b = reinterpret_cast<const float*>(smem + S::heads) + 640;
   tc_fence_before();
-  __syncthreads();
+  if (pair) cluster_sync_all();  // the peer's barriers are initialised before anything is sent to them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp >= kWarpProd0) {
     // ------------------------------------------------ weight producers
     IssueBars IB{bar_w_full, bar_w_empty, bar_token, sbase + S::ring};
-    producer_loop<kStages>(tab, IB, args.packed, TileSeq{nullptr, (int64_t)blockIdx.x, (int64_t)gridDim.x, n_tiles}, warp - kWarpProd0, lane);
+    producer_loop<kStages>(tab, IB, args.packed, seq, warp - kWarpProd0, lane, pair_rank);
   } else if (warp >= kWarpMma) {
     // ------------------------------------------------ MMA issuers (mlp_issue.cuh)
     // Within a layer the encoding chunk (smem operand, independent of the previous epilogue)
     // goes FIRST in the table: it fills the bubble while the epilogue converts chunk 0.
     if (tmem_base != 0) __trap();  // 512 columns = the whole tensor memory
     IssueBars IB{bar_w_full, bar_w_empty, bar_token, sbase + S::ring};
-    issuer_loop<kStages>(tab, IB, sbase, TileSeq{nullptr, (int64_t)blockIdx.x, (int64_t)gridDim.x, n_tiles}, (uint32_t)(warp - kWarpMma), lane, args.trace);
+    issuer_loop<kStages>(tab, IB, sbase, seq, (uint32_t)(warp - kWarpMma), lane, args.trace, pair);
   } else if (warp >= kWarpEnc0) {
     // ------------------------------------------------ encoders (thread = sample row)
     const int row = (warp - kWarpEnc0) * 32 + lane;
     uint32_t titer = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
+    for (int64_t tile; (tile = seq.get(titer)) >= 0; ++titer) {
       const int64_t p = tile * kTileM + row;
       const bool valid = p < args.n_samples;
+      const bool real = tile < n_tiles;
       float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
       if (valid) {
         if (args.x) {
@@ -208,7 +218,7 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar_pos_full);
-        if (kTrain) {
+        if (kTrain && real) {
           const int slab = (warp - kWarpEnc0) * kSlabBytes2;
           bulk_s2g(stash_tile + prog.stash_aux_pos_off + slab, sbase + S::aux_pos + slab, kSlabBytes2);
           bulk_commit();
@@ -222,7 +232,7 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(bar_dir_full);
-          if (kTrain) {
+          if (kTrain && real) {
             const int slab = (warp - kWarpEnc0) * kSlabBytes2;
             bulk_s2g(stash_tile + prog.stash_aux_dir_off + slab, sbase + S::aux_dir + slab, kSlabBytes2);
             bulk_commit();
@@ -242,9 +252,10 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
     uint32_t acc_phase[2] = {0, 0};
     uint32_t n_staged = 0;
     uint32_t titer = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
+    for (int64_t tile; (tile = seq.get(titer)) >= 0; ++titer) {
       const int64_t p = tile * kTileM + row;
       const bool valid = p < args.n_samples;
+      const bool real = tile < n_tiles;
       uint8_t* stash_tile = kTrain ? args.stash + (size_t)tile * prog.stash_tile_bytes : nullptr;
       float sigma = 0.f;
       for (int g = 0; g < n_gemm; ++g) {
@@ -319,7 +330,7 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
             if (lane == 0) mbar_arrive(bar_a_ready + 8 * c);
           }
           if (kTrain) {
-            if (L.mask_off >= 0) {
+            if (L.mask_off >= 0 && real) {
               // 1-bit ReLU mask of these 32 features (what dgrad reads instead of the activations):
               // one word per row, 128 B per warp store
               uint32_t bits = 0;
@@ -336,7 +347,7 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
             fence_proxy_async_smem();
             if (issuer) bulk_wait_read1();  // slabs older than the previous one have been read
             named_bar_sync(1 + quarter, 64);
-            if (issuer) {
+            if (issuer && real) {
               bulk_s2g(stash_tile + L.stash_off + c * kChunkBytes + quarter * kSlabBytes2, buf, kSlabBytes2);
               bulk_commit();
             }
@@ -369,7 +380,8 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
     if (issuer) bulk_wait0();
   }
   tc_fence_before();
-  __syncthreads();
+  if (pair) cluster_sync_all();  // the peer's last commits arrive on this CTA's barriers: stay until it is done
+  else __syncthreads();
   if (warp == kWarpMma) tmem_dealloc(tmem_base, kTmemCols2);
 }
 
@@ -455,12 +467,31 @@ int mlp_forward_v2(const MlpProgram& P, const void* packed, int64_t n_samples, i
       if ((g & 1) == ((n_gemm - 1) & 1)) ++T.last_acc_n;
   }
   const int64_t n_tiles = (n_samples + kTileM - 1) / kTileM;
-  const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
-FsProfScope prof_(stash ? "mlp_fwd_train" : "mlp_fwd", stream);
-  if (stash)
-    mlp_fwd2_kernel<true><<<grid, kThreads2, Smem<true>::total, (cudaStream_t)stream>>>(P, a, T);
-  else
-    mlp_fwd2_kernel<false><<<grid, kThreads2, Smem<false>::total, (cudaStream_t)stream>>>(P, a, T);
+  static const int pair_env = [] { const char* e = getenv("FSNERF_FWD_PAIR"); return e ? atoi(e) : 0; }();
+  a.pair = (pair_env != 0 && n_tiles >= 2) ? 1 : 0;
+  int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
+  if (a.pair) grid = (grid + 1) & ~1;  // whole pairs (kNumSMs is even); the odd CTA may run dummies only
+  FsProfScope prof_(stash ? "mlp_fwd_train" : "mlp_fwd", stream);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads2);
+    cfg.dynamicSmemBytes = stash ? Smem<true>::total : Smem<false>::total;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = a.pair ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = stash ? cudaLaunchKernelEx(&cfg, mlp_fwd2_kernel<true>, P, a, T)
+                          : cudaLaunchKernelEx(&cfg, mlp_fwd2_kernel<false>, P, a, T);
+    if (e != cudaSuccess) {
+      fsnerf_set_error("mlp_forward: launch: %s", cudaGetErrorString(e));
+      return FSNERF_ERR_CUDA;
+    }
+  }
   return fsnerf_check_launch("mlp_forward");
 }
 

@@ -87,18 +87,23 @@ __host__ __device__ __forceinline__ uint32_t relu_bits_word_off(int chunk, int h
 }
 
 // ------------------------------------------------------------------ tile sequence of a CTA
-// Static: tiles first, first + stride, ... < n_tiles.  Dynamic (feed != nullptr): one thread of the
+// Static: n_iters tiles first, first + stride, ...  Dynamic (feed != nullptr): one thread of the
 // CTA claims tiles from a global counter a little ahead of their use and publishes them in shared
 // memory: feed[0] = tiles claimed so far (monotonic), feed[1 + (i & 3)] = tile of iteration i or -1
 // when the work has run out.  Every role warp asks for iteration i and gets the same answer.
+// A static sequence may run past n_tiles (CTA pairs sharing multicast weight stages must do the
+// same number of iterations): such a tile is a dummy — computed, never stored.
 struct TileSeq {
   volatile int* feed;
   int64_t first, stride, n_tiles;
+  int64_t n_iters;  // static sequences only
+  __device__ __forceinline__ static TileSeq strided(int64_t first, int64_t stride, int64_t n_tiles, int64_t lead) {
+    // `lead`: the CTA whose iteration count this one follows (itself, or the even CTA of its pair)
+    const int64_t n = lead < n_tiles ? (n_tiles - lead + stride - 1) / stride : 0;
+    return TileSeq{nullptr, first, stride, n_tiles, n};
+  }
   __device__ __forceinline__ int64_t get(uint32_t titer) const {
-    if (feed == nullptr) {
-      const int64_t t = first + (int64_t)titer * stride;
-      return t < n_tiles ? t : -1;
-    }
+    if (feed == nullptr) return (int64_t)titer < n_iters ? first + (int64_t)titer * stride : -1;
     uint32_t spins = 0;
     while (feed[0] <= (int)titer) {
       __nanosleep(32);
@@ -109,7 +114,7 @@ struct TileSeq {
   // "is there a tile for iteration titer", for a warp that must stay provably converged (the MMA
   // issuers): exits and result are warp votes
   __device__ __forceinline__ bool has_converged(uint32_t titer) const {
-    if (feed == nullptr) return first + (int64_t)titer * stride < n_tiles;
+    if (feed == nullptr) return (int64_t)titer < n_iters;
     uint32_t spins = 0;
     while (!__all_sync(0xffffffffu, feed[0] > (int)titer)) {
       if (++spins > (1u << 26)) {
@@ -123,9 +128,13 @@ struct TileSeq {
 
 // ------------------------------------------------------------------ weight producers
 // Producer `me` of kProdWarps streams every kProdWarps-th stage: L2 -> smem, one bulk copy.
+// pair_rank >= 0: this CTA is one of a cluster pair running the same chunk sequence in lock step.
+// A stage is free when BOTH CTAs' MMAs have released it (w_empty counts two multicast commits),
+// each CTA arms its own w_full barrier, and ONE of the two (rank = chunk parity) fetches the
+// operand from L2 for both: half the L2 -> SM weight traffic.
 template <int kStages>
 __device__ __forceinline__ void producer_loop(const IssueTable& tab, const IssueBars& B, const uint8_t* packed,
-                                              const TileSeq& seq, int me, int lane) {
+                                              const TileSeq& seq, int me, int lane, int pair_rank = -1) {
   uint32_t cnt = 0;
   for (uint32_t titer = 0; seq.get(titer) >= 0; ++titer) {
     for (int j = 0; j < tab.n; ++j, ++cnt) {
@@ -135,8 +144,12 @@ __device__ __forceinline__ void producer_loop(const IssueTable& tab, const Issue
       if (lane == 0) {
         const uint32_t bytes = tab.rec[j].w_bytes;
         mbar_arrive_expect_tx(B.w_full + 8 * stage, bytes);
-        bulk_g2s(B.ring + stage * kStageBytes, packed + (size_t)tab.rec[j].w_block * kBlockBytes, bytes,
-                 B.w_full + 8 * stage);
+        if (pair_rank < 0)
+          bulk_g2s(B.ring + stage * kStageBytes, packed + (size_t)tab.rec[j].w_block * kBlockBytes, bytes,
+                   B.w_full + 8 * stage);
+        else if ((int)(cnt & 1u) == pair_rank)
+          bulk_g2s_multicast(B.ring + stage * kStageBytes, packed + (size_t)tab.rec[j].w_block * kBlockBytes, bytes,
+                             B.w_full + 8 * stage, (uint16_t)3);
       }
       __syncwarp();
     }
@@ -168,7 +181,8 @@ __device__ __forceinline__ void producer_loop_thread(const IssueTable& tab, cons
 // clock64 timeline [tile iteration < 4][layer][k]: k = 0 layer reached, 1 first MMA, 2 committed.
 template <int kStages>
 __device__ __forceinline__ void issuer_loop(const IssueTable& tab, const IssueBars& B, uint32_t sbase,
-                                            const TileSeq& seq, uint32_t me, int lane, long long* trace) {
+                                            const TileSeq& seq, uint32_t me, int lane, long long* trace,
+                                            bool pair = false) {
   const uint32_t issue = (lane == 0) ? 1u : 0u;
   const int n_rec = tab.n;
   uint32_t titer = 0;
@@ -206,7 +220,8 @@ __device__ __forceinline__ void issuer_loop(const IssueTable& tab, const IssueBa
     }
     if (lane == 0) mbar_arrive(B.token + 8 * (me ^ 1u));  // the last MMA is queued: hand over
     __syncwarp();
-    umma_commit_conv(B.w_empty + 8 * stage, issue);
+    if (pair) umma_commit_multicast_conv(B.w_empty + 8 * stage, issue, (uint16_t)3);
+    else umma_commit_conv(B.w_empty + 8 * stage, issue);
     if (R.xbar) umma_commit_conv(sbase + R.xbar, issue);
     const uint32_t n_acc = R.n_acc;
     if (n_acc) {

@@ -56,3 +56,13 @@ names = ["slot_wait", "slot_ok", "done", "published", "scouted", "issued", "rele
 print("image q (tile iter * 10 + image): " + " ".join(f"{n:>10s}" for n in names) + "   (us; images with two readers have no issue/release stamps)")
 for q in list(range(0, 40)) + list(range(100, 120)):
     print(f"  q={q:3d} " + " ".join(f"{(e[k, q] - t0) / 1e3:10.1f}" if e[k, q] > 0 else "         -" for k in range(7)))
+
+# dgrad CTA 0, per tile iteration and step: cycles relative to the tile's first stamp
+tl = trace.cpu()[:4 * 16 * 8].view(4, 16, 8).double()
+print("dgrad CTA 0 timeline (cycles from the tile's first stamp): issuer reached layer, first MMA issued, layer committed | "
+      "epilogue starts waiting, accumulator full, epilogue done")
+for it in range(1, 4):
+    base = tl[it][tl[it] > 0].min() if (tl[it] > 0).any() else 0
+    for s_ in range(12):
+        if (tl[it, s_] > 0).any():
+            print(f"  tile {it} step/layer {s_:2d}: " + " ".join(f"{(tl[it, s_, k] - base):9.0f}" if tl[it, s_, k] > 0 else "        -" for k in range(6)))
