@@ -209,7 +209,8 @@ struct StatClock {
 
 // =========================================================================== dgrad role
 __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog, const PlanB& plan,
-                                          const ArgsB& args, const IssueTable& tab, const RingB& ring) {
+                                          const ArgsB& args, const IssueTable& tab, const RingB& ring,
+                                          const int my_id) {
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_w_full = sbase + BarsB::w_full;
@@ -232,7 +233,7 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
   // the slowest one.
   volatile int* feed = reinterpret_cast<volatile int*>(smem + BarsB::feed);
   const TileSeq seq{feed, 0, 0, n_tiles};
-  long long* stats = args.trace ? args.trace + kStatBase + 8 * blockIdx.x : nullptr;
+  long long* stats = args.trace ? args.trace + kStatBase + 8 * my_id : nullptr;
   const long long t_begin = stats ? clock64() : 0;
 
   if (threadIdx.x == 0) {
@@ -275,8 +276,8 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
     // next is only freed by readers of an image published here).  The arrivals release their
     // stores at CTA scope; the fence below makes the publication cumulative at GPU scope.
     if (lane == 0) {
-      uint32_t* my_prod = ring.prod + blockIdx.x;
-      int32_t* my_tiles = ring.tile_of + (size_t)blockIdx.x * ring.row_cap;
+      uint32_t* my_prod = ring.prod + my_id;
+      int32_t* my_tiles = ring.tile_of + (size_t)my_id * ring.row_cap;
       int n_claimed = 0;
       bool dry = false;
       auto claim_upto = [&](int want) {  // tiles of iterations < want are known
@@ -284,7 +285,7 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
           int t = -1;
           if (!dry && n_claimed < ring.row_cap - 1) {
             // (FSNERF_DEBUG_FLAGS & 16: the static split blockIdx, blockIdx + n_d, ... for A/B runs)
-            const int64_t c = (ring.debug & 16) ? (int64_t)blockIdx.x + (int64_t)n_claimed * ring.n_d
+            const int64_t c = (ring.debug & 16) ? (int64_t)my_id + (int64_t)n_claimed * ring.n_d
                                                 : (int64_t)atomicAdd(ring.tile_ctr, 1u);
             if (c < n_tiles) t = (int)c;
           }
@@ -301,9 +302,9 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
         claim_upto(it + 3);  // iteration it + 2: the weight producers / MMA issuers run up to ~1 tile ahead
         for (int k = 0; k < ring.n_img; ++k, ++q) {
           mbar_wait_relaxed(bar_img_done + 8 * (q % kImgBars), (q / kImgBars) & 1);
-          if (blockIdx.x == 0) evt(args.trace, EVT_DONE, q);
+          if (my_id == 0) evt(args.trace, EVT_DONE, q);
           st_release_u32(my_prod, q + 1);  // release = fence.acq_rel.gpu + store
-          if (blockIdx.x == 0) evt(args.trace, EVT_PUB, q);
+          if (my_id == 0) evt(args.trace, EVT_PUB, q);
         }
       }
       // end marker: the iteration after the last reads as published and its tile_of entry is -1
@@ -323,8 +324,8 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
     // images are taken by the wgrad CTAs, which have every image in shared memory anyway).
     const int quarter = warp - kWarpRed0;
     const uint32_t stage_base = sbase + SmemB::staging + quarter * (kStageBufsB * kSlabBytesB);
-    uint8_t* my_ring = ring.base + (size_t)blockIdx.x * ring.depth * kImgSlotBytes;
-    uint32_t* my_cons = ring.cons + (size_t)blockIdx.x * ring.depth;
+    uint8_t* my_ring = ring.base + (size_t)my_id * ring.depth * kImgSlotBytes;
+    uint32_t* my_cons = ring.cons + (size_t)my_id * ring.depth;
     uint32_t n_staged = 0;
     uint32_t q = 0;  // image sequence number of this CTA
     uint32_t cons_seen = 0;  // the upcoming slot's counter, fetched (acquire) one image ahead by lane 0
@@ -338,11 +339,11 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
         uint8_t* img = my_ring + (size_t)slot * kImgSlotBytes;
         if (gen > 0) {  // every reader of the slot's previous image has landed it in its smem
           sc.start();
-          if (sc.on && blockIdx.x == 0) evt(args.trace, EVT_SLOT_WAIT, q);
+          if (sc.on && my_id == 0) evt(args.trace, EVT_SLOT_WAIT, q);
           if (lane == 0 && (int32_t)(cons_seen - 2u * gen) < 0)
             wait_counter_ge(my_cons + slot, 2u * gen, "dpre ring slot");
           __syncwarp();
-          if (sc.on && blockIdx.x == 0) evt(args.trace, EVT_SLOT_OK, q);
+          if (sc.on && my_id == 0) evt(args.trace, EVT_SLOT_OK, q);
           sc.stop(st_cons);
         }
         for (int c = 0; c < nchunk; ++c, ++n_staged) {
@@ -478,13 +479,13 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
         const bool add_sigma = S.add_sigma != 0;
         // chunk 0's mask does not depend on the MMAs: fetch it before waiting on the accumulator
         uint32_t mw = mimg ? __ldg(reinterpret_cast<const uint32_t*>(mimg + relu_bits_word_off(0, half, row))) : 0xFFFFFFFFu;
-        if (threadIdx.x == 0 && args.trace && blockIdx.x == 0 && titer < 4) args.trace[(titer * 16 + s) * 8 + 3] = clock64();
+        if (threadIdx.x == 0 && args.trace && my_id == 0 && titer < 4) args.trace[(titer * 16 + s) * 8 + 3] = clock64();
         ec.start();
         mbar_wait(bar_acc_full + 8 * r, acc_phase[r]);
         ec.stop(st_acc);
         acc_phase[r] ^= 1;
         tc_fence_after();
-        if (threadIdx.x == 0 && args.trace && blockIdx.x == 0 && titer < 4) args.trace[(titer * 16 + s) * 8 + 4] = clock64();
+        if (threadIdx.x == 0 && args.trace && my_id == 0 && titer < 4) args.trace[(titer * 16 + s) * 8 + 4] = clock64();
         // The accumulator loads are software-pipelined one chunk ahead through two register
         // buffers: chunk c+1 is in flight from tensor memory while chunk c is converted, masked,
         // written back as the next step's A operand and staged for the ring.
@@ -527,7 +528,7 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
           chunk(c, va, vb);
           chunk(c + 1, vb, va);
         }
-        if (threadIdx.x == 0 && args.trace && blockIdx.x == 0 && titer < 4) args.trace[(titer * 16 + s) * 8 + 5] = clock64();
+        if (threadIdx.x == 0 && args.trace && my_id == 0 && titer < 4) args.trace[(titer * 16 + s) * 8 + 5] = clock64();
       }
     }
     if (ec.on) { stats[3] = st_stage; stats[4] = st_acc; }
@@ -546,7 +547,7 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
 
 // =========================================================================== wgrad role
 __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog, const ArgsB& args,
-                                          const WgradPlan& plan, const RingB& ring) {
+                                          const WgradPlan& plan, const RingB& ring, const int cta) {
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_full = sbase + kWSmemBars;
@@ -560,7 +561,6 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
   volatile uint32_t* ready_upto = reinterpret_cast<volatile uint32_t*>(smem + kWSmemBars + 160);
   volatile uint32_t* released_upto = reinterpret_cast<volatile uint32_t*>(smem + kWSmemBars + 164);
   volatile uint32_t* queue = reinterpret_cast<volatile uint32_t*>(smem + kWSmemQueue);
-  const int cta = (int)blockIdx.x - ring.n_d;
   int j = 0;
   while (j + 1 < plan.n_jobs && cta >= plan.job[j + 1].cta_begin) ++j;
   const WgradJob& J = plan.job[j];
@@ -583,7 +583,7 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
     __threadfence_block();
     return true;
   };
-  long long* stats = args.trace ? args.trace + kStatBase + 8 * blockIdx.x : nullptr;
+  long long* stats = args.trace ? args.trace + kStatBase + 8 * (ring.n_d + cta) : nullptr;
   const long long t_begin = stats ? clock64() : 0;
   // head jobs also stage the slab's rows of out / d_out (fp32 [P,4]): 1 KB each behind the operand chunks
   const uint32_t aux_off = (uint32_t)(J.a_chunks + J.b_chunks + J.c_chunks) * kSlabBytes;
@@ -948,19 +948,31 @@ mlp_bwd_fused_kernel(const __grid_constant__ MlpProgram prog, const __grid_const
                      const __grid_constant__ WgradPlan wplan, const __grid_constant__ RingB ring) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
+  // Roles by contiguous block ranges.  Consecutive block indices land on the two SMs of one TPC
+  // (measured: blockIdx 2k, 2k+1 -> smid 2j, 2j+1), so with an even n_d both SMs of a TPC run the
+  // SAME role.  Interleaving the roles (one dgrad + one wgrad CTA per TPC, to spread the wgrad
+  // role's ~2.5x heavier L2 ingest) was measured much SLOWER: 5.65 vs 3.76 ms per C2 launch on the
+  // same box, some wgrad CTAs then see 6-8 k cycles per stage copy instead of 3-4 k.
+  const int b = (int)blockIdx.x;
+  const bool is_d = b < ring.n_d;
+  const int id = is_d ? b : b - ring.n_d;
+  const int lin = is_d ? id : ring.n_d + id;  // index of this CTA's tuning records
   if (args.trace && threadIdx.x == 0) {  // tuning aid: CTA life span on the global timer (ns)
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    args.trace[6144 + 2 * blockIdx.x] = (long long)t;
+    args.trace[6144 + 2 * lin] = (long long)t;
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    args.trace[6500 + lin] = (long long)smid;
   }
-  if ((int)blockIdx.x < ring.n_d)
-    dgrad_cta(smem, prog, plan, args, tab, ring);
+  if (is_d)
+    dgrad_cta(smem, prog, plan, args, tab, ring, id);
   else
-    wgrad_cta(smem, prog, args, wplan, ring);
+    wgrad_cta(smem, prog, args, wplan, ring, id);
   if (args.trace && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    args.trace[6144 + 2 * blockIdx.x + 1] = (long long)t;
+    args.trace[6144 + 2 * lin + 1] = (long long)t;
   }
 }
 

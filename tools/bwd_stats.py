@@ -66,3 +66,26 @@ for it in range(1, 4):
     for s_ in range(12):
         if (tl[it, s_] > 0).any():
             print(f"  tile {it} step/layer {s_:2d}: " + " ".join(f"{(tl[it, s_, k] - base):9.0f}" if tl[it, s_, k] > 0 else "        -" for k in range(6)))
+
+# placement: which SM each CTA of the last launch ran on, and what its TPC sibling (smid ^ 1) did
+smid = trace.cpu()[6500:6500 + 148].tolist()
+role = {int(sm): ("d" if b < n_d else "w") for b, sm in enumerate(smid)}
+print("blockIdx -> smid:", " ".join(f"{b}:{int(sm)}" for b, sm in enumerate(smid)))
+import collections
+pairs = collections.Counter("".join(sorted(role.get(sm, "-") + role.get(sm ^ 1, "-"))) for sm in role if sm % 2 == 0 or (sm ^ 1) not in role)
+print("TPC role pairs:", dict(pairs))
+for sib in ("w", "d"):
+    m = torch.tensor([role.get(int(smid[n_d + i]) ^ 1, "-") == sib for i in range(n_w)])
+    if m.any():
+        r = wg[m]
+        print(f"wgrad CTAs whose TPC sibling is {sib}: n={int(m.sum())} MMA full-wait {r[:, 3].mean():8.1f} kcyc, issue->landed {(r[:, 5] / (2 * r[:, 4])).mean():6.0f} cyc, ready-wait {r[:, 1].mean():8.1f}")
+for sib in ("w", "d"):
+    m = torch.tensor([role.get(int(smid[i]) ^ 1, "-") == sib for i in range(n_d)])
+    if m.any():
+        r = dg[m]
+        print(f"dgrad CTAs whose TPC sibling is {sib}: n={int(m.sum())} cons wait {r[:, 1].mean():8.1f} staging wait {r[:, 3].mean():8.1f} acc wait {r[:, 4].mean():8.1f}")
+
+print("wgrad CTAs: id job smid total ready-wait empty-wait full-wait issue->landed")
+for i in range(n_w):
+    r = wg[i]
+    print(f"  {i:3d} {int(round(float(r[6]) * 1e3)):3d} {int(smid[n_d + i]):4d} {r[0]:8.1f} {r[1]:8.1f} {r[2]:8.1f} {r[3]:8.1f} {float(r[5] / (2 * r[4])):7.0f}")
