@@ -212,7 +212,7 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
                                           const ArgsB& args, const IssueTable& tab, const RingB& ring,
                                           const int my_id) {
   const uint32_t sbase = smem_u32(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // (shuffle: provably warp-uniform)
   const uint32_t bar_w_full = sbase + BarsB::w_full;
   const uint32_t bar_w_empty = sbase + BarsB::w_empty;
   const uint32_t bar_a_ready = sbase + BarsB::a_ready;
@@ -549,7 +549,7 @@ __device__ __forceinline__ void dgrad_cta(uint8_t* smem, const MlpProgram& prog,
 __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog, const ArgsB& args,
                                           const WgradPlan& plan, const RingB& ring, const int cta) {
   const uint32_t sbase = smem_u32(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // (shuffle: provably warp-uniform)
   const uint32_t bar_full = sbase + kWSmemBars;
   const uint32_t bar_empty = bar_full + 8 * kWMaxStages;
   const uint32_t bar_acc_full = bar_empty + 8 * kWMaxStages;
@@ -888,7 +888,7 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
           mc.stop(st_full);
           if (mc.on) st_lat += clock64() - issue_clk[stage];
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {  // (elected, not `lane == 0`: the compiler then knows one thread issues)
             const uint32_t sa = sbase + stage * stage_bytes, sb = sa + (uint32_t)J.a_chunks * kSlabBytes;
             for (int mh = 0; mh < n_mh; ++mh) {
 #pragma unroll
@@ -904,7 +904,7 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
           __syncwarp();
         }
       }
-      if (lane == 0) umma_commit(bar_acc_full);
+      if (elect_one()) umma_commit(bar_acc_full);  // the same thread every time: it issued the MMAs
       __syncwarp();
       if (mc.on) { stats[3] = st_full; stats[4] = n_done; stats[6] = j; stats[5] = st_lat; }
     }

@@ -89,10 +89,10 @@ struct Fwd2Args {
   int density_only;
   float* out;
   uint8_t* stash;
-  int pair;  // launched as clusters of two CTAs sharing multicast weight stages
+  int pair;  // launched as clusters of two CTAs whose MMAs are cta_group::2 (M = 256 over both SMs)
 };
 
-template <bool kTrain>
+template <bool kTrain, bool kPair>
 __global__ void __launch_bounds__(kThreads2, 1)
 mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ Fwd2Args args,
                 const __grid_constant__ IssueTable tab) {
@@ -100,7 +100,7 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
   using S = Smem<kTrain>;
   constexpr int kStages = n_stages<kTrain>();
   const uint32_t sbase = smem_u32(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // (shuffle: provably warp-uniform)
   using B = Bars<kTrain>;
   const uint32_t bar_w_full = sbase + B::w_full;       // [kStages]
   const uint32_t bar_w_empty = sbase + B::w_empty;     // [kStages]
@@ -120,10 +120,13 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
   for (int g = 0; g < prog.n_hidden; ++g)
     if (prog.layer[g].use_aux) last_pos_user = g;
   const int64_t n_tiles = (args.n_samples + kTileM - 1) / kTileM;
-  // CTA pairs (args.pair): the two CTAs of a cluster stream the SAME weight chunks in lock step,
-  // each fetching every other one from L2 for both (mlp_issue.cuh: producer_loop).  Both run the
-  // even CTA's iteration count; a tile index past the end is a dummy (computed, not stored).
-  const bool pair = args.pair != 0;
+  // CTA pairs (args.pair): the two CTAs of a cluster work on two tiles as ONE M = 256 problem.
+  // Rank 0 issues tcgen05.mma.cta_group::2 for both; every weight operand is split by N between
+  // the two SMs' shared memories, so each SM fetches HALF the weight bytes per tile — the layer
+  // period of the single-CTA kernel is set by the 32 KB-per-chunk weight stream into the SM
+  // (~665 cycles per chunk at ~50 B/clk, measured), not by the 512 cycles of MMAs.  Both CTAs run
+  // the even CTA's iteration count; a tile index past the end is a dummy (computed, not stored).
+  constexpr bool pair = kPair;
   const int pair_rank = pair ? (int)cluster_ctarank() : -1;
   const TileSeq seq = TileSeq::strided((int64_t)blockIdx.x, (int64_t)gridDim.x, n_tiles,
                                        (int64_t)blockIdx.x - (pair ? pair_rank : 0));
@@ -134,23 +137,29 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(bar_w_full + 8 * s, 1);
-      mbar_init(bar_w_empty + 8 * s, pair ? 2 : 1);  // pair: released by both CTAs' MMAs
+      mbar_init(bar_w_full + 8 * s, (pair && pair_rank == 0) ? 2 : 1);  // leader: + the peer's relay
+      mbar_init(bar_w_empty + 8 * s, 1);
     }
-    for (int c = 0; c < 4; ++c) mbar_init(bar_a_ready + 8 * c, kEpiWarps);
+    // the leader's operand barriers count the warps of both CTAs
+    for (int c = 0; c < 4; ++c) mbar_init(bar_a_ready + 8 * c, pair ? 2 * kEpiWarps : kEpiWarps);
     mbar_init(bar_acc_full, kMmaWarps);
     mbar_init(bar_acc_full + 8, kMmaWarps);
     mbar_init(bar_token, 1);
     mbar_init(bar_token + 8, 1);
-    mbar_init(bar_pos_full, kEncWarps);
+    mbar_init(bar_pos_full, pair ? 2 * kEncWarps : kEncWarps);
     mbar_init(bar_pos_empty, 1);
-    mbar_init(bar_dir_full, kEncWarps);
+    mbar_init(bar_dir_full, pair ? 2 * kEncWarps : kEncWarps);
     mbar_init(bar_dir_empty, 1);
     fence_barrier_init();
   }
   if (warp == kWarpMma) {
-    tmem_alloc(tmem_slot, kTmemCols2);
-    tmem_relinquish();
+    if constexpr (pair) {
+      tmem_alloc_pair(tmem_slot, kTmemCols2);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols2);
+      tmem_relinquish();
+    }
   }
   // biases: constant bank -> shared memory (the epilogue reads them as broadcast LDS.128;
   // indexed constant loads miss the small constant cache and serialise the epilogue)
@@ -177,7 +186,10 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
     // goes FIRST in the table: it fills the bubble while the epilogue converts chunk 0.
     if (tmem_base != 0) __trap();  // 512 columns = the whole tensor memory
     IssueBars IB{bar_w_full, bar_w_empty, bar_token, sbase + S::ring};
-    issuer_loop<kStages>(tab, IB, sbase, seq, (uint32_t)(warp - kWarpMma), lane, args.trace, pair);
+    if (pair_rank <= 0)
+      issuer_loop<kStages, kPair>(tab, IB, sbase, seq, (uint32_t)(warp - kWarpMma), lane, args.trace);
+    else if (warp == kWarpMma)  // peer CTA: its MMAs are issued by the leader
+      weight_relay_loop<kStages>(tab, IB, seq, lane);
   } else if (warp >= kWarpEnc0) {
     // ------------------------------------------------ encoders (thread = sample row)
     const int row = (warp - kWarpEnc0) * 32 + lane;
@@ -217,7 +229,8 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(bar_pos_full);
+        if (pair_rank > 0) mbar_arrive_cluster(cluster_map_shared(bar_pos_full, 0));  // release: the tile is in this CTA's smem
+        else mbar_arrive(bar_pos_full);
         if (kTrain && real) {
           const int slab = (warp - kWarpEnc0) * kSlabBytes2;
           bulk_s2g(stash_tile + prog.stash_aux_pos_off + slab, sbase + S::aux_pos + slab, kSlabBytes2);
@@ -231,7 +244,8 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(bar_dir_full);
+          if (pair_rank > 0) mbar_arrive_cluster(cluster_map_shared(bar_dir_full, 0));
+          else mbar_arrive(bar_dir_full);
           if (kTrain && real) {
             const int slab = (warp - kWarpEnc0) * kSlabBytes2;
             bulk_s2g(stash_tile + prog.stash_aux_dir_off + slab, sbase + S::aux_dir + slab, kSlabBytes2);
@@ -249,6 +263,7 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t stage_base = sbase + S::staging + quarter * (kStageBufs * kSlabBytes2);
     const bool issuer = kTrain && half == 0 && lane == 0;
+    const uint32_t a_ready_leader = pair ? cluster_map_shared(bar_a_ready, 0) : bar_a_ready;
     uint32_t acc_phase[2] = {0, 0};
     uint32_t n_staged = 0;
     uint32_t titer = 0;
@@ -327,7 +342,11 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_a_ready + 8 * c);
+            if (lane == 0) {
+              // (the operand is in tensor memory and its store has been waited for: no memory release)
+              if (pair_rank > 0) mbar_arrive_cluster_relaxed(a_ready_leader + 8 * c);
+              else mbar_arrive(bar_a_ready + 8 * c);
+            }
           }
           if (kTrain) {
             if (L.mask_off >= 0 && real) {
@@ -382,7 +401,10 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
   tc_fence_before();
   if (pair) cluster_sync_all();  // the peer's last commits arrive on this CTA's barriers: stay until it is done
   else __syncthreads();
-  if (warp == kWarpMma) tmem_dealloc(tmem_base, kTmemCols2);
+  if (warp == kWarpMma) {
+    if constexpr (pair) tmem_dealloc_pair(tmem_base, kTmemCols2);
+    else tmem_dealloc(tmem_base, kTmemCols2);
+  }
 }
 
 }  // namespace
@@ -396,14 +418,19 @@ int mlp_forward_v2(const MlpProgram& P, const void* packed, int64_t n_samples, i
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-      cudaError_t e1 = cudaFuncSetAttribute(mlp_fwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaError_t e1 = cudaFuncSetAttribute(mlp_fwd2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             Smem<false>::total);
-      cudaError_t e2 = cudaFuncSetAttribute(mlp_fwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaError_t e2 = cudaFuncSetAttribute(mlp_fwd2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             Smem<true>::total);
-      if (e1 != cudaSuccess || e2 != cudaSuccess) {
-        fsnerf_set_error("mlp_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-        return FSNERF_ERR_CUDA;
-      }
+      cudaError_t e3 = cudaFuncSetAttribute(mlp_fwd2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            Smem<false>::total);
+      cudaError_t e4 = cudaFuncSetAttribute(mlp_fwd2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            Smem<true>::total);
+      for (cudaError_t e : {e1, e2, e3, e4})
+        if (e != cudaSuccess) {
+          fsnerf_set_error("mlp_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+          return FSNERF_ERR_CUDA;
+        }
       if (dev >= 0 && dev < 64) configured[dev] = true;
     }
   }
@@ -415,6 +442,10 @@ int mlp_forward_v2(const MlpProgram& P, const void* packed, int64_t n_samples, i
   a.x = x; a.dirs = dirs; a.mask_pos = mask_pos; a.mask_dir = mask_dir;
   a.density_only = density_only; a.out = out; a.stash = reinterpret_cast<uint8_t*>(stash);
   FS_REQUIRE(P.n_gemm <= kMaxLayers2, "mlp_forward: at most %d GEMM layers are supported", kMaxLayers2);
+  const int64_t n_tiles = (n_samples + kTileM - 1) / kTileM;
+  static const int pair_env = [] { const char* e = getenv("FSNERF_FWD_PAIR"); return e ? atoi(e) : 0; }();
+  const bool pair_launch = pair_env != 0 && n_tiles >= 2;
+  a.pair = pair_launch ? 1 : 0;
   IssueTable T;
   T.pad = 0;
   {
@@ -451,7 +482,7 @@ int mlp_forward_v2(const MlpProgram& P, const void* packed, int64_t n_samples, i
           if (is_dir) R.xbar = bar(Bars<true>::dir_empty, Bars<false>::dir_empty);
           else if (g == last_pos_user) R.xbar = bar(Bars<true>::pos_empty, Bars<false>::pos_empty);
         }
-        R.idesc = (L.n_halves == 2) ? umma_idesc_bf16(128, 256, 0, 0) : umma_idesc_bf16(128, 128, 0, 0);
+        R.idesc = umma_idesc_bf16(pair_launch ? 256 : 128, L.n_halves == 2 ? 256 : 128, 0, 0);
         R.accbar = bar(Bars<true>::acc_full, Bars<false>::acc_full) + 8 * (g & 1);
         R.n_acc = issue_n_acc(i, nch);
         R.w_block = (uint32_t)(L.first_block + (c >= 0 ? c : L.n_act_chunks) * L.n_halves);
@@ -466,9 +497,6 @@ int mlp_forward_v2(const MlpProgram& P, const void* packed, int64_t n_samples, i
     for (int g = 0; g < n_gemm; ++g)
       if ((g & 1) == ((n_gemm - 1) & 1)) ++T.last_acc_n;
   }
-  const int64_t n_tiles = (n_samples + kTileM - 1) / kTileM;
-  static const int pair_env = [] { const char* e = getenv("FSNERF_FWD_PAIR"); return e ? atoi(e) : 0; }();
-  a.pair = (pair_env != 0 && n_tiles >= 2) ? 1 : 0;
   int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
   if (a.pair) grid = (grid + 1) & ~1;  // whole pairs (kNumSMs is even); the odd CTA may run dummies only
   FsProfScope prof_(stash ? "mlp_fwd_train" : "mlp_fwd", stream);
@@ -485,8 +513,13 @@ int mlp_forward_v2(const MlpProgram& P, const void* packed, int64_t n_samples, i
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = stash ? cudaLaunchKernelEx(&cfg, mlp_fwd2_kernel<true>, P, a, T)
-                          : cudaLaunchKernelEx(&cfg, mlp_fwd2_kernel<false>, P, a, T);
+    cudaError_t e;
+    if (a.pair)
+      e = stash ? cudaLaunchKernelEx(&cfg, mlp_fwd2_kernel<true, true>, P, a, T)
+                : cudaLaunchKernelEx(&cfg, mlp_fwd2_kernel<false, true>, P, a, T);
+    else
+      e = stash ? cudaLaunchKernelEx(&cfg, mlp_fwd2_kernel<true, false>, P, a, T)
+                : cudaLaunchKernelEx(&cfg, mlp_fwd2_kernel<false, false>, P, a, T);
     if (e != cudaSuccess) {
       fsnerf_set_error("mlp_forward: launch: %s", cudaGetErrorString(e));
       return FSNERF_ERR_CUDA;

@@ -128,10 +128,12 @@ struct TileSeq {
 
 // ------------------------------------------------------------------ weight producers
 // Producer `me` of kProdWarps streams every kProdWarps-th stage: L2 -> smem, one bulk copy.
-// pair_rank >= 0: this CTA is one of a cluster pair running the same chunk sequence in lock step.
-// A stage is free when BOTH CTAs' MMAs have released it (w_empty counts two multicast commits),
-// each CTA arms its own w_full barrier, and ONE of the two (rank = chunk parity) fetches the
-// operand from L2 for both: half the L2 -> SM weight traffic.
+// pair_rank >= 0: this CTA is one of a cluster pair whose MMAs are cta_group::2 instructions issued
+// by rank 0.  Each CTA fetches ITS N-half of every weight operand (the packed image stores an
+// operand as N-halves of 128 rows, a 128-row operand as one block whose 64-row halves are its two
+// 8 KB halves) into its own ring; a stage is free in both CTAs when the leader's commit has
+// arrived (multicast).  The leader learns that the peer's half has landed from the peer's relay
+// warp (weight_relay_loop): its w_full barriers count two arrivals.
 template <int kStages>
 __device__ __forceinline__ void producer_loop(const IssueTable& tab, const IssueBars& B, const uint8_t* packed,
                                               const TileSeq& seq, int me, int lane, int pair_rank = -1) {
@@ -142,15 +144,32 @@ __device__ __forceinline__ void producer_loop(const IssueTable& tab, const Issue
       const uint32_t stage = cnt % kStages, phase = (cnt / kStages) & 1;
       mbar_wait_relaxed(B.w_empty + 8 * stage, phase ^ 1);
       if (lane == 0) {
-        const uint32_t bytes = tab.rec[j].w_bytes;
+        uint32_t bytes = tab.rec[j].w_bytes;
+        const uint8_t* src = packed + (size_t)tab.rec[j].w_block * kBlockBytes;
+        if (pair_rank >= 0) {
+          bytes >>= 1;
+          src += (size_t)pair_rank * bytes;
+        }
         mbar_arrive_expect_tx(B.w_full + 8 * stage, bytes);
-        if (pair_rank < 0)
-          bulk_g2s(B.ring + stage * kStageBytes, packed + (size_t)tab.rec[j].w_block * kBlockBytes, bytes,
-                   B.w_full + 8 * stage);
-        else if ((int)(cnt & 1u) == pair_rank)
-          bulk_g2s_multicast(B.ring + stage * kStageBytes, packed + (size_t)tab.rec[j].w_block * kBlockBytes, bytes,
-                             B.w_full + 8 * stage, (uint16_t)3);
+        bulk_g2s(B.ring + stage * kStageBytes, src, bytes, B.w_full + 8 * stage);
       }
+      __syncwarp();
+    }
+  }
+}
+
+// Peer CTA of a pair (rank 1), one warp: as each of this CTA's weight halves lands, arrive on the
+// LEADER's barrier of that stage.
+template <int kStages>
+__device__ __forceinline__ void weight_relay_loop(const IssueTable& tab, const IssueBars& B, const TileSeq& seq,
+                                                  int lane) {
+  uint32_t cnt = 0;
+  const uint32_t leader_w_full = cluster_map_shared(B.w_full, 0);
+  for (uint32_t titer = 0; seq.get(titer) >= 0; ++titer) {
+    for (int j = 0; j < tab.n; ++j, ++cnt) {
+      const uint32_t stage = cnt % kStages, phase = (cnt / kStages) & 1;
+      mbar_wait(B.w_full + 8 * stage, phase);
+      if (lane == 0) mbar_arrive_cluster_relaxed(leader_w_full + 8 * stage);
       __syncwarp();
     }
   }
@@ -179,11 +198,12 @@ __device__ __forceinline__ void producer_loop_thread(const IssueTable& tab, cons
 // All 32 lanes of issuer `me` run this loop in lock step on provably uniform values; the
 // tcgen05 instructions are guarded so that lane 0 alone issues them.  trace: optional
 // clock64 timeline [tile iteration < 4][layer][k]: k = 0 layer reached, 1 first MMA, 2 committed.
-template <int kStages>
+// kPair: the cta_group::2 forms (a kernel that contains them can only be launched as clusters of
+// two, so the single-CTA kernels must not instantiate this path).
+template <int kStages, bool kPair = false>
 __device__ __forceinline__ void issuer_loop(const IssueTable& tab, const IssueBars& B, uint32_t sbase,
-                                            const TileSeq& seq, uint32_t me, int lane, long long* trace,
-                                            bool pair = false) {
-  const uint32_t issue = (lane == 0) ? 1u : 0u;
+                                            const TileSeq& seq, uint32_t me, int lane, long long* trace) {
+  constexpr bool pair = kPair;
   const int n_rec = tab.n;
   uint32_t titer = 0;
   int j = (int)me;
@@ -201,34 +221,62 @@ __device__ __forceinline__ void issuer_loop(const IssueTable& tab, const IssueBa
     const uint32_t b0 = umma_desc_lo(B.ring + stage * kStageBytes);
     const uint32_t apar = (((flags & kRecParTile) ? titer : 0u) ^ (flags >> kRecParShift)) & 1u;
     if (tr && first && titer < 4) trace[(titer * 16 + g_cur) * 8 + 0] = clock64();
-    mbar_wait_converged(B.w_full + 8 * stage, wpar);
-    mbar_wait_converged(sbase + R.abar, apar);
+    if constexpr (pair) {  // (the peer CTA's relay, epilogue and encoder warps arrive on these too)
+      mbar_wait_converged_cluster(B.w_full + 8 * stage, wpar);
+      mbar_wait_converged_cluster(sbase + R.abar, apar);
+    } else {
+      mbar_wait_converged(B.w_full + 8 * stage, wpar);
+      mbar_wait_converged(sbase + R.abar, apar);
+    }
     mbar_wait_converged(B.token + 8 * me, tok_par);  // the other issuer has queued its chunk
     tok_par ^= 1u;
     tc_fence_after();
     if (tr && first && titer < 4) trace[(titer * 16 + g_cur) * 8 + 1] = clock64();
-    if (is_tmem) {  // features [0,32) of the chunk at columns +0, +8; [32,64) at +32, +40
-      umma_bf16_ts_conv(d_col, a0, umma_desc_from_lo(b0), idesc, first ? 0u : 1u, issue);
-      umma_bf16_ts_conv(d_col, a0 + 8, umma_desc_from_lo(b0 + 2), idesc, 1u, issue);
-      umma_bf16_ts_conv(d_col, a0 + 32, umma_desc_from_lo(b0 + 4), idesc, 1u, issue);
-      umma_bf16_ts_conv(d_col, a0 + 40, umma_desc_from_lo(b0 + 6), idesc, 1u, issue);
-    } else {
-      umma_bf16_ss_conv(d_col, umma_desc_from_lo(a0), umma_desc_from_lo(b0), idesc, first ? 0u : 1u, issue);
-      umma_bf16_ss_conv(d_col, umma_desc_from_lo(a0 + 2), umma_desc_from_lo(b0 + 2), idesc, 1u, issue);
-      umma_bf16_ss_conv(d_col, umma_desc_from_lo(a0 + 4), umma_desc_from_lo(b0 + 4), idesc, 1u, issue);
-      umma_bf16_ss_conv(d_col, umma_desc_from_lo(a0 + 6), umma_desc_from_lo(b0 + 6), idesc, 1u, issue);
-    }
-    if (lane == 0) mbar_arrive(B.token + 8 * (me ^ 1u));  // the last MMA is queued: hand over
-    __syncwarp();
-    if (pair) umma_commit_multicast_conv(B.w_empty + 8 * stage, issue, (uint16_t)3);
-    else umma_commit_conv(B.w_empty + 8 * stage, issue);
-    if (R.xbar) umma_commit_conv(sbase + R.xbar, issue);
     const uint32_t n_acc = R.n_acc;
-    if (n_acc) {
-      umma_commit_conv(sbase + R.accbar, issue);
-      if (n_acc > 1) umma_commit_conv(sbase + R.accbar, issue);
-      if (tr && (flags & kRecLast) && titer < 4) trace[(titer * 16 + g_cur) * 8 + 2] = clock64();
+    const uint32_t acc0 = first ? 0u : 1u;
+    if (elect_one()) {  // one thread issues the chunk's MMAs, the hand-over and the completion arrivals
+      if constexpr (pair) {
+        if (is_tmem) {
+          umma_bf16_ts_pair(d_col, a0, umma_desc_from_lo(b0), idesc, acc0);
+          umma_bf16_ts_pair(d_col, a0 + 8, umma_desc_from_lo(b0 + 2), idesc, 1u);
+          umma_bf16_ts_pair(d_col, a0 + 32, umma_desc_from_lo(b0 + 4), idesc, 1u);
+          umma_bf16_ts_pair(d_col, a0 + 40, umma_desc_from_lo(b0 + 6), idesc, 1u);
+        } else {
+          umma_bf16_ss_pair(d_col, umma_desc_from_lo(a0), umma_desc_from_lo(b0), idesc, acc0);
+          umma_bf16_ss_pair(d_col, umma_desc_from_lo(a0 + 2), umma_desc_from_lo(b0 + 2), idesc, 1u);
+          umma_bf16_ss_pair(d_col, umma_desc_from_lo(a0 + 4), umma_desc_from_lo(b0 + 4), idesc, 1u);
+          umma_bf16_ss_pair(d_col, umma_desc_from_lo(a0 + 6), umma_desc_from_lo(b0 + 6), idesc, 1u);
+        }
+      } else if (is_tmem) {  // features [0,32) of the chunk at columns +0, +8; [32,64) at +32, +40
+        umma_bf16_ts(d_col, a0, umma_desc_from_lo(b0), idesc, acc0);
+        umma_bf16_ts(d_col, a0 + 8, umma_desc_from_lo(b0 + 2), idesc, 1u);
+        umma_bf16_ts(d_col, a0 + 32, umma_desc_from_lo(b0 + 4), idesc, 1u);
+        umma_bf16_ts(d_col, a0 + 40, umma_desc_from_lo(b0 + 6), idesc, 1u);
+      } else {
+        umma_bf16_ss(d_col, umma_desc_from_lo(a0), umma_desc_from_lo(b0), idesc, acc0);
+        umma_bf16_ss(d_col, umma_desc_from_lo(a0 + 2), umma_desc_from_lo(b0 + 2), idesc, 1u);
+        umma_bf16_ss(d_col, umma_desc_from_lo(a0 + 4), umma_desc_from_lo(b0 + 4), idesc, 1u);
+        umma_bf16_ss(d_col, umma_desc_from_lo(a0 + 6), umma_desc_from_lo(b0 + 6), idesc, 1u);
+      }
+      mbar_arrive(B.token + 8 * (me ^ 1u));  // the last MMA is queued: hand over
+      if constexpr (pair) {  // completions arrive in both CTAs
+        umma_commit_pair(B.w_empty + 8 * stage);
+        if (R.xbar) umma_commit_pair(sbase + R.xbar);
+        if (n_acc) {
+          umma_commit_pair(sbase + R.accbar);
+          if (n_acc > 1) umma_commit_pair(sbase + R.accbar);
+        }
+      } else {
+        umma_commit(B.w_empty + 8 * stage);
+        if (R.xbar) umma_commit(sbase + R.xbar);
+        if (n_acc) {
+          umma_commit(sbase + R.accbar);
+          if (n_acc > 1) umma_commit(sbase + R.accbar);
+        }
+      }
     }
+    __syncwarp();
+    if (n_acc && tr && (flags & kRecLast) && titer < 4) trace[(titer * 16 + g_cur) * 8 + 2] = clock64();
     // next chunk of mine
     j += kMmaWarps;
     stage += kMmaWarps;
