@@ -290,7 +290,8 @@ mlp_fwd2_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
         // rolled on purpose: the kernel's hot loops must stay instruction-cache resident
         // (the MMA issue loop shares the SM's I-cache with this code).  Pipelining the
         // accumulator loads one chunk ahead through a second register buffer (as the dgrad
-        // epilogue does) was measured SLOWER here: 1.54 -> 1.71 ms per training forward.
+        // epilogue does) was measured SLOWER here, twice: 1.54 -> 1.71 ms per training forward in
+        // round 1, 1.65 -> 1.85 ms (inference 13.1 -> 13.4 ms per 12.6 M samples) after the MMA issue fix.
 #pragma unroll 1
         for (int c = 0; c < nchunk; ++c) {
           const int c0 = 64 * c + 32 * half;  // first feature handled by this thread
