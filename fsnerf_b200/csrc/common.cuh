@@ -192,16 +192,6 @@ __device__ __forceinline__ void mbar_wait_converged_cluster(uint32_t bar, uint32
     }
   }
 }
-// one L2 read delivered to the same shared-memory offset of every CTA in cta_mask; each
-// destination CTA's barrier (same offset) receives the complete_tx for its copy
-__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes,
-                                                   uint32_t bar, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::
-          "r"(dst_smem),
-      "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
-      : "memory");
-}
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
                "r"(src_smem), "r"(bytes)
@@ -314,6 +304,11 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// cta_group::2: ONE instruction, issued by the leader CTA of a pair, computes M = 256 rows — 128
+// from each CTA's tensor memory (A, D at the same addresses in both) — against an N-wide B whose
+// two N/2 halves sit at the same shared-memory offset of the two CTAs: each SM fetches and holds
+// half of every weight operand.  Completions (commit) arrive on the barrier at the same offset in
+// BOTH CTAs.
 __device__ __forceinline__ void umma_bf16_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                                   uint32_t accumulate) {
   asm volatile(
@@ -338,10 +333,11 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       "h"((uint16_t)3)
       : "memory");
 }
-// Converged-issue forms: executed by ALL lanes of the issuing warp with warp-uniform
-// operands (they stay in uniform registers: no R2UR/ELECT waterfall per instruction) and
-// a per-lane guard that is true for one lane only.  Measured (tools/mma_bench.cu):
-// 128.0 cycles per M=128 N=256 K=16 MMA vs 138 issue-bound cycles from a lane-0 branch.
+// Converged-issue forms: executed by ALL lanes of the issuing warp with a per-lane guard that is
+// true for one lane only.  In the micro-benchmark (tools/mma_bench.cu) the operands stayed in
+// uniform registers (128.0 cycles per M=128 N=256 K=16 MMA vs 138 from a lane-0 branch); in the
+// real kernels the compiler still wrapped each one in an ELECT + R2UR.BROADCAST loop, so the MLP
+// kernels issue from `if (elect_one())` instead (above).  Kept for the benchmarks.
 __device__ __forceinline__ void umma_bf16_ts_conv(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b,
                                                   uint32_t idesc, uint32_t accumulate, uint32_t issue) {
   asm volatile(
@@ -360,39 +356,6 @@ __device__ __forceinline__ void umma_bf16_ss_conv(uint32_t tmem_d, uint64_t desc
       "setp.ne.b32 e, %5, 0;\n\t"
       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
-      : "memory");
-}
-// cta_group::2: ONE instruction, issued by the leader CTA of a pair, computes M = 256 rows — 128
-// from each CTA's tensor memory (A, D at the same addresses in both) — against an N-wide B whose
-// two N/2 halves sit at the same shared-memory offset of the two CTAs: each SM fetches and holds
-// half of every weight operand.
-__device__ __forceinline__ void umma_bf16_ts_pair_conv(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b,
-                                                       uint32_t idesc, uint32_t accumulate, uint32_t issue) {
-  asm volatile(
-      "{\n\t.reg .pred p, e;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 e, %5, 0;\n\t"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16_ss_pair_conv(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
-                                                       uint32_t idesc, uint32_t accumulate, uint32_t issue) {
-  asm volatile(
-      "{\n\t.reg .pred p, e;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 e, %5, 0;\n\t"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
-      : "memory");
-}
-// ... and its completion arrives on the barrier at this offset in BOTH CTAs
-__device__ __forceinline__ void umma_commit_pair_conv(uint32_t bar, uint32_t issue) {
-  asm volatile(
-      "{\n\t.reg .pred e;\n\t"
-      "setp.ne.b32 e, %1, 0;\n\t"
-      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %2;\n\t}" ::"r"(bar),
-      "r"(issue), "h"((uint16_t)3)
       : "memory");
 }
 // Two MMAs with two NON-BLOCKING mbarrier probes slotted between them (converged issue).
@@ -452,15 +415,6 @@ __device__ __forceinline__ void umma_commit_conv(uint32_t bar, uint32_t issue) {
       "setp.ne.b32 e, %1, 0;\n\t"
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar),
       "r"(issue)
-      : "memory");
-}
-// ... arriving on the barrier at this offset in every CTA of cta_mask
-__device__ __forceinline__ void umma_commit_multicast_conv(uint32_t bar, uint32_t issue, uint16_t cta_mask) {
-  asm volatile(
-      "{\n\t.reg .pred e;\n\t"
-      "setp.ne.b32 e, %1, 0;\n\t"
-      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %2;\n\t}" ::"r"(bar),
-      "r"(issue), "h"(cta_mask)
       : "memory");
 }
 // registers -> TMEM: thread i of the warp writes lane (taddr.lane + i), 16 consecutive columns

@@ -8,9 +8,15 @@
 //    bookkeeping (operand waits, descriptors, commits: 400+ cycles of dependent
 //    uniform-datapath instructions) inside the 512 cycles of its four MMAs, so TWO warps
 //    alternate chunks and pass a token right after their last MMA issue.
-//  * operands of tcgen05 instructions must be provably warp-uniform or the compiler wraps
-//    every instruction in an ELECT + 6x R2UR.BROADCAST waterfall: the chunk table is a
-//    __grid_constant__ kernel parameter, waits exit on warp votes, TMEM base is 0.
+//  * tcgen05 instructions take their operands from UNIFORM registers.  Issued under a per-lane
+//    guard (`@lane0 tcgen05.mma`, or inside `if (lane == 0)`) the compiler cannot know that one
+//    thread is active and wraps EVERY instruction in an ELECT + 6x R2UR.BROADCAST loop: ~160
+//    cycles per MMA at issue, above the 128 it takes to execute (round 1 and most of round 2
+//    shipped that: 650 cycles per 64-wide K chunk instead of 512).  Inside `if (elect_one())`
+//    (elect.sync) the operands move with plain R2UR ahead of four back-to-back UTCHMMA: the
+//    inference forward went from 14.0 to 12.7 ms per 12.6 M samples (76 % -> 84 % of the sustained
+//    bf16 peak).  The chunk table is a __grid_constant__ kernel parameter (uniform loads), the
+//    waits exit on warp votes, the warp index comes from a shuffle.
 //  * bulk copies issued by one thread do not overlap (~440 cycles each, any size <= 32 KB):
 //    two producer warps, 32 KB stages.
 #pragma once

@@ -11,7 +11,7 @@ import sys
 so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fsnerf_b200", "libfsnerf_b200.so")
 out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
 WATCH = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UTMALDG", "UTMASTG", "UTCCP", "HMMA", "HGMMA",
-         "SYNCS", "LDGSTS", "RED", "ATOMG", "ATOMS", "MEMBAR", "FENCE", "CCTL", "LDS", "STS", "LDG", "STG", "MUFU", "SHFL"]
+         "R2UR.BROADCAST", "ELECT", "SYNCS", "LDGSTS", "RED", "ATOMG", "ATOMS", "MEMBAR", "FENCE", "CCTL", "LDS", "STS", "LDG", "STG", "MUFU", "SHFL"]
 kern, counts, total = None, collections.OrderedDict(), collections.Counter()
 for line in out.splitlines():
     m = re.match(r"\s*Function : (\S+)", line)
@@ -22,7 +22,7 @@ for line in out.splitlines():
         kern = re.sub(r"\(.*", "", kern)
         counts[kern] = collections.Counter()
         continue
-    m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
+    m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", line)
     if m and kern:
         op = m.group(1)
         total[kern] += 1
@@ -32,7 +32,9 @@ for line in out.splitlines():
                 break
 print("SASS opcode counts per kernel of fsnerf_b200/libfsnerf_b200.so (cuobjdump -sass, sm_100a)")
 print("no kernel uses tensor-map TMA (UTMALDG / UTMASTG): operand images are pre-swizzled in global memory and moved by")
-print("plain bulk copies (cp.async.bulk = UBLKCP), completion on mbarriers (SYNCS); no legacy HMMA / HGMMA anywhere.\n")
+print("plain bulk copies (cp.async.bulk = UBLKCP), completion on mbarriers (SYNCS); no legacy HMMA / HGMMA anywhere.")
+print("R2UR.BROADCAST / ELECT: the per-instruction uniform-operand loops; after the elect.sync issue fix the MLP kernels keep them")
+print("only around bulk copies issued by several lanes of one warp (by design), not around UTCHMMA.\n")
 for k, c in counts.items():
     print(f"{k}  [{total[k]} instructions]")
     print("   " + "  ".join(f"{w}={c[w]}" for w in WATCH if c[w]))
