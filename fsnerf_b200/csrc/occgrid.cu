@@ -102,7 +102,10 @@ __global__ void __launch_bounds__(kWarps * 32) occgrid_march_kernel(const MarchA
     }
   }
   const float near = a.near_planes ? a.near_planes[r] : a.near;
-  const float t_begin = fmaxf(near, t0), t_limit = fminf(a.far, t1);
+  // The samples lie on the lattice near + k * step anchored at the ray's OWN near plane (which
+  // carries the stratified jitter): a ray that meets the box behind its near plane starts at the
+  // first lattice point at or after the entry, so the jitter survives for cameras outside the box.
+  const float t_begin = fmaf(ceilf(fmaxf(t0 - near, 0.f) / a.step), a.step, near), t_limit = fminf(a.far, t1);
   int total = 0;
   const int64_t base = a.offsets ? a.offsets[r] : 0;
   if (!miss && t_limit > t_begin) {

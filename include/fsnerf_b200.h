@@ -128,7 +128,8 @@ int fsnerf_encode(int64_t n_points, int d_input, int n_freqs, const float* freqs
 /* Replaces nerfacc's OccGridEstimator.sampling as called at
  * src/render/rendering.py:66-74 (ray/box slab test + fixed-step marching through
  * binaries[levels][res][res][res], z fastest; aabbs [levels][6], level l encloses l-1).
- * Interval k = [t_begin + k*step, +step), t_begin = max(near plane, box entry); kept iff
+ * Interval k = [t_begin + k*step, +step), t_begin = the first point of the lattice near + j*step
+ * (anchored at the ray's near plane) at or after the box entry; kept iff
  * its midpoint is before min(far, box exit) and in an occupied cell of the finest level
  * containing it.  near_planes [n_rays] (per-ray, jittered when stratified) or NULL -> near.
  * Count pass: offsets == NULL, writes counts[n_rays].  Fill pass: offsets = exclusive scan

@@ -6,8 +6,9 @@ src/run-nerf.py:92-98,288-295).  Its source is NOT on the box and it has no test
 vectors in the reference — **parity unpinned**.  This file states the semantics the CUDA kernels
 (fsnerf_b200/csrc/occgrid.cu) implement, following nerfacc's published behaviour:
 
-* ``march``: per ray, slab test against the outermost level's box; t_begin = max(near plane
-  (+ U[0,1)*step when stratified), entry), t_limit = min(far plane, exit); candidate interval
+* ``march``: per ray, slab test against the outermost level's box; t_begin = the first point of
+  the lattice near + j*step — near = the ray's near plane (+ U[0,1)*step when stratified) — at or
+  after the entry, t_limit = min(far plane, exit); candidate interval
   k = [t_begin + k*step, +step) is emitted iff its midpoint is < t_limit and lies in an occupied
   cell of the finest level whose box contains it (cell = floor((p - min)/(max - min) * res),
   x-major / z-fastest).  Output is ray-major packed.  fp32 arithmetic in the kernel's order
@@ -65,7 +66,11 @@ def march(rays_o, rays_d, binaries, aabbs, step, near=0.0, far=1e10, near_planes
             elif o[k] < b[k] or o[k] > b[3 + k]:
                 miss = True
         nr = f32(near if near_planes is None else near_planes[r])
-        t_begin, t_limit = max(nr, t0), min(f32(far), t1)
+        # lattice nr + k * step anchored at the ray's own (jittered) near plane: first point at or
+        # after the box entry (csrc/occgrid.cu; nerfacc 0.5.3's traversal keeps its running t on
+        # that lattice too — parity unpinned, see the module header)
+        t_begin = _fma(f32(np.ceil(max(t0 - nr, f32(0)) / step)), step, nr)
+        t_limit = min(f32(far), t1)
         if miss or not t_limit > t_begin:
             continue
         n_cand = int(min(np.ceil((t_limit - t_begin) / step), 1.0e7))

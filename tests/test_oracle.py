@@ -404,8 +404,9 @@ def test_occgrid_oracle_known_answers():
     np.testing.assert_array_equal(ri, [0, 0, 0, 0, 1, 1, 1, 1])
     np.testing.assert_allclose(ts[:4], [2.5, 2.625, 2.75, 2.875])
     np.testing.assert_allclose(te - ts, 0.125)
-    # jitter below the entry distance has no effect (near plane = 0 + u*step < 2): same samples
-    np.testing.assert_array_equal(ts[4:], ts[:4])
+    # the lattice is anchored at the ray's own near plane (0 + u*step), not at the box entry, so the
+    # stratified jitter survives for a camera outside the box: 0.0625 + k/8 with midpoints in [2.5,3)
+    np.testing.assert_allclose(ts[4:], [2.4375, 2.5625, 2.6875, 2.8125])
     # camera inside the box: the lattice starts at the (jittered) near plane
     ri2, ts2, _ = oocc.march(np.array([[0.25, 0.25, -0.75]], np.float32), d[:1], binaries, aabbs[:1], 0.125,
                              near_planes=np.array([0.0625], np.float32))
