@@ -115,12 +115,14 @@ struct RingB {
 };
 
 // ------------------------------------------------------------------ wgrad role layout
-constexpr int kSlabRows = 64;                     // samples per stage
+constexpr int kSlabRows = 64;                     // samples per stage (32: measured 3.40 vs 3.34 ms; the side-warp paths assume 64)
+constexpr int kSlabsPerTile = kTileM / kSlabRows;
+constexpr int kIssueLanes = 2 * kSlabsPerTile;    // issuing lanes of each of the four producer warps (8 threads per slab)
 constexpr int kSlabBytes = kSlabRows * 128;       // 8 KB per 64-feature chunk
 // A stage holds one 64-sample slab of the job's operands: (a_chunks + b_chunks) x 8 KB, so the
 // small jobs (encoding parts, branch) get a deeper ring out of the same 192 KB: their per-tile
 // work is a few hundred cycles and only tiles in flight hide the load latency.
-constexpr int kWRingBytes = 24 * kSlabBytes + 3 * 2048;  // 3 stages of a [256 x 256] job (+ its out / d_out rows)
+constexpr int kWRingBytes = 24 * 8192 + 3 * 2048;  // 3 stages of a [256 x 256] job (+ its out / d_out rows)
 constexpr int kWMaxStages = 8;
 constexpr int kWSmemBars = kWRingBytes;            // full[8], empty[8], acc_full, TMEM slot, queue counters
 constexpr int kWQueue = 64;                        // tile queue entries (scout -> issuers / releaser)
@@ -621,8 +623,8 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
       // (8 KB each: 64 rows of one chunk image) are spread over SIXTEEN issuing threads — lanes
       // 0..3 of warps 2, 3 take the tile's first slab, those of warps 4, 5 its second — each arming
       // its stage's barrier for its own bytes: at most one or two copies per thread and tile.
-      const int pw = (warp - 2) * 4 + lane;  // issuing thread index (lanes 0..3 issue)
-      const int my_slab = (warp - 2) >> 1, my_c = pw & 7;
+      const int pw = (warp - 2) * kIssueLanes + lane;  // issuing thread index (lanes 0..kIssueLanes-1 issue)
+      const int my_slab = ((warp - 2) * kIssueLanes) >> 3, my_c = pw & 7;  // (one slab per warp or per warp pair)
       const int n_cp = J.a_chunks + J.b_chunks + J.c_chunks;
       uint32_t fenced_upto = 0;
       StatClock pc{0, stats != nullptr && warp == 2 && lane == 0};
@@ -631,12 +633,12 @@ __device__ __forceinline__ void wgrad_cta(uint8_t* smem, const MlpProgram& prog,
         pc.start();
         if (!have_tile(n)) break;  // (every lane: the warp stays together)
         pc.stop(st_ready);
-        const uint32_t cnt = 2u * n + (uint32_t)my_slab;
+        const uint32_t cnt = (uint32_t)kSlabsPerTile * n + (uint32_t)my_slab;
         const uint32_t stage = cnt % n_stages, phase = (cnt / n_stages) & 1;
         pc.start();
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
         pc.stop(st_empty);
-        if (lane < 4) {
+        if (lane < kIssueLanes) {
           if (n >= fenced_upto) {
             // one generic -> async proxy fence covers every tile the scout has published so far
             const uint32_t r = *ready_upto;
