@@ -10,15 +10,28 @@ from fsnerf_b200.engine import HotPath  # noqa: E402
 
 dev = torch.device("cuda:0")
 hp = HotPath(device=dev)
-R = 16384
+R = int(os.environ.get("R", "16384"))
 g = torch.Generator().manual_seed(0)
 o = (torch.tensor([0.0, 0, 4.0]) + 0.05 * torch.randn(R, 3, generator=g)).to(dev)
 d = torch.nn.functional.normalize(torch.tensor([0.0, 0, -1.0]) + 0.3 * torch.randn(R, 3, generator=g), dim=-1).to(dev)
-hp.render(o, d)
+TRAIN = os.environ.get("TRAIN", "0") == "1"  # TRAIN=1: the training forward (stash + masks written)
+
+
+def run():
+    if not TRAIN:
+        return hp.render(o, d)
+    S = 192
+    ts, te = ops.sample_stratified(R, S, 2.0, 6.0, None, device=dev)
+    hp._pack()
+    stash = torch.empty(ops.mlp_stash_bytes(hp.cfg, R * S), dtype=torch.uint8, device=dev)
+    return ops.mlp_forward(hp.cfg, hp.net_params(1), hp.packed[1], rays_o=o, rays_d=d, t_starts=ts, t_ends=te, stash=stash)
+
+
+run()
 torch.cuda.synchronize()
 trace = torch.zeros(2048, dtype=torch.int64, device=dev)
 _lib.load().fsnerf_debug_set_trace(_lib.ptr(trace))
-hp.render(o, d)
+run()
 torch.cuda.synchronize()
 _lib.load().fsnerf_debug_set_trace(None)
 tall = trace.cpu()
