@@ -196,7 +196,8 @@ def ncu_traffic(kernel):
     if not files:
         return None, None
     d = json.load(open(files[-1]))
-    key = {"mlp_fwd_train": "mlp_fwd2_kernel<1>", "mlp_fwd": "mlp_fwd2_kernel<0>"}.get(kernel, kernel)
+    # (the forward's template arguments: <train> in older captures, <train, pair> since r02c)
+    key = {"mlp_fwd_train": "mlp_fwd2_kernel<1", "mlp_fwd": "mlp_fwd2_kernel<0"}.get(kernel, kernel)
     rows = [r for k, v in d.items() if k.startswith(key) for r in v]
     if not rows:
         return None, None
