@@ -24,6 +24,18 @@ from .parallel import allreduce_gradients, loss_grad_scale
 _M64 = (1 << 64) - 1
 
 
+def jitter_seeds(seed: int, rank: int, draw: int):
+    """Keys of the (stratified, pdf) uniform streams of one step: splitmix64 of (construction
+    seed, rank, draw counter), so ranks and steps never share a stream."""
+    keys = []
+    for which in (0, 1):
+        z = (seed * 0x9E3779B97F4A7C15 + (rank << 40) + 2 * draw + which) & _M64
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+        keys.append(z ^ (z >> 31))
+    return keys
+
+
 class HotPath:
     def __init__(self, n_coarse=64, n_fine=128, near=2.0, far=6.0, white_bkgd=True, device="cuda",
                  n_layers=8, d_hidden=256, skip=(4,), n_freqs=10, n_freqs_dir=4, log_space=True,
@@ -129,16 +141,9 @@ class HotPath:
 
     # ------------------------------------------------------------------ forward
     def _jitter_seeds(self):
-        """Two fresh 64-bit keys (stratified, pdf) for the in-kernel uniform stream: splitmix64 of
-        (construction seed, rank, draw counter), so ranks and steps never share a stream."""
+        """Two fresh 64-bit keys (stratified, pdf) for the in-kernel uniform stream."""
         self._draws += 1
-        keys = []
-        for which in (0, 1):
-            z = (self._seed * 0x9E3779B97F4A7C15 + (self.rank << 40) + 2 * self._draws + which) & _M64
-            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
-            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
-            keys.append(z ^ (z >> 31))
-        return keys
+        return jitter_seeds(self._seed, self.rank, self._draws)
 
     def _forward(self, rays_o, rays_d, u_strat, u_pdf, train, seeds=(None, None)):
         cfg, R = self.cfg, rays_o.shape[0]

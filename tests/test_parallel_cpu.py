@@ -129,3 +129,17 @@ def test_allreduce_module_gradients(tmp_path):
     assert torch.equal(r["flat"], want)
     assert torch.equal(r["a"], want[0:6].view(3, 2)) and torch.equal(r["b"], want[8:13])
     assert torch.equal(r["w"], torch.full((3, 4), 3.0)) and torch.equal(r["bias"], torch.full((3,), 3.0))
+
+
+def test_jitter_seed_streams_are_distinct():
+    """engine.jitter_seeds: every (rank, step, sampler) gets its own 64-bit key, reproducibly"""
+    from fsnerf_b200.engine import jitter_seeds
+    keys = set()
+    for rank in range(8):
+        for draw in range(1, 200):
+            a, b = jitter_seeds(42, rank, draw)
+            assert 0 <= a < (1 << 64) and 0 <= b < (1 << 64)
+            keys.update((a, b))
+    assert len(keys) == 8 * 199 * 2
+    assert jitter_seeds(42, 3, 17) == jitter_seeds(42, 3, 17)
+    assert jitter_seeds(42, 3, 17) != jitter_seeds(43, 3, 17)
